@@ -1,0 +1,242 @@
+/*
+ * nvfi_b200 — C ABI of the B200-native NVFi render + velocity-advection hot path.
+ *
+ * The reference (vLAR-group/NVFi) has NO native interface: its hot path is pure
+ * Python/PyTorch behind `models/__init__.py`.  This header is the
+ * drop-in boundary a native replacement exports: plain C structs holding device
+ * pointers and scalars, `extern "C"` entry points taking a `cudaStream_t` (passed as
+ * `void*`), no torch types, no global state.  Each entry point cites the reference
+ * function(s) it replaces.  `nvfi_b200/_lib.py` binds it with ctypes;
+ * `nvfi_b200/models/` mirrors the reference's Python surface on top.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the name ends in `_host`.
+ *   - All arrays are dense, row-major, float32 unless noted.
+ *   - Every function returns 0 on success, a negative NVFI_E* code on argument
+ *     errors, or a positive cudaError_t value if a CUDA call failed.
+ *   - Functions only enqueue work on `stream`; they never synchronise, except the
+ *     `*_host` variants which copy results back and synchronise the stream.
+ *   - Factor planes are consumed in a packed channels-last layout (H, W, R) produced
+ *     by nvfi_pack_plane from the reference's NCHW parameter (1, R, H, W)
+ *     (models/tensorf_keyframe.py:143-149); MLP weights in a transposed, zero-padded
+ *     layout produced by nvfi_pack_linear from nn.Linear's (out, in).
+ */
+#ifndef NVFI_B200_H
+#define NVFI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NVFI_ABI_VERSION 3
+
+/* error codes */
+#define NVFI_OK 0
+#define NVFI_EINVAL (-1)      /* bad argument (null pointer, negative size) */
+#define NVFI_EUNSUPPORTED (-2) /* shape/config outside what the kernels implement */
+
+/* enums */
+#define NVFI_ACT_SOFTPLUS 0 /* fea2denseAct, models/tensorf_keyframe.py:320-325 */
+#define NVFI_ACT_RELU 1
+#define NVFI_ACT_RELU_ABS 2
+
+#define NVFI_SHADING_MLP_PE 0 /* models/tensorf_base.py:67-98 */
+#define NVFI_SHADING_SH 1     /* models/tensorf_model_utils.py:292-296 */
+
+#define NVFI_GATE_AABB 0 /* VelocityAABB,    models/velocity_field.py:21-33 */
+#define NVFI_GATE_SUR 1  /* VelocityAABBSur, models/velocity_field.py:36-51 */
+
+#define NVFI_HIDDEN 128      /* width of every hidden layer on the path */
+#define NVFI_VEL_IN 28       /* PositionEncoder(3) on xyzt, models/base_network.py:42-54 */
+#define NVFI_VEL_LAYERS 6    /* models/velocity_field.py:58-67 */
+#define NVFI_MAX_MASK_LAYERS 8
+#define NVFI_MAX_MASK_DIM 32
+
+/* One packed dense layer: wt is (k_pad, n_pad) row-major = W^T zero padded,
+ * bias is (n_pad) zero padded (or NULL).  Produced by nvfi_pack_linear. */
+typedef struct NvfiLinear {
+  const float* wt;
+  const float* bias;
+  int32_t in_dim, out_dim; /* logical sizes */
+  int32_t k_pad, n_pad;    /* padded sizes: k_pad % 32 == 0, n_pad % 4 == 0 */
+} NvfiLinear;
+
+/* Everything the render path reads.  Mirrors the attributes of
+ * TensorVMKeyframeTimeKplane (models/tensorf_keyframe.py:38-114) and TensorBase
+ * (models/tensorf_base.py:134-183) that the hot path touches. */
+typedef struct NvfiField {
+  /* geometry (models/tensorf_base.py:214-227, 241-242) */
+  float aabb_min[3], aabb_max[3];
+  float inv_aabb[3]; /* 2 / (aabb_max - aabb_min), FP32 as computed by torch */
+  int32_t grid[3];   /* gridSize (x, y, z) */
+  int32_t num_keyframes;
+  float tmax;
+  float time_scale; /* tmax / (K - 1), or 1 */
+  float dt_max;     /* 0.5 * tmax / (K - 1), or 1  (models/tensorf_keyframe.py:577) */
+  float near, far;
+  float step_size;
+  int32_t n_samples;
+  /* density / appearance decode */
+  float density_shift, distance_scale, weight_thres;
+  int32_t fea2dense_act;
+  int32_t shading_mode;
+  int32_t pos_pe, view_pe;
+  int32_t rd, ra, app_dim; /* components per plane, appearance feature width */
+  /* packed planes (H, W, R).  space k: H = grid[m1], W = grid[m0] with
+   * matModeSpace = [[0,1],[0,2],[1,2]]; time k: H = K, W = grid[n0] with
+   * matModeTime = [[2,3],[1,3],[0,3]]  (models/tensorf_keyframe.py:39-40) */
+  const float* dplane_space[3];
+  const float* dplane_time[3];
+  const float* aplane_space[3];
+  const float* aplane_time[3];
+  NvfiLinear basis_mat;     /* Ra -> app_dim, no bias (models/tensorf_keyframe.py:129-131) */
+  NvfiLinear render_mlp[3]; /* MLPRender_PE: in -> 128 -> 128 -> 3 */
+  /* velocity field (models/velocity_field.py:54-98) */
+  int32_t use_vel;
+  NvfiLinear vel_net[NVFI_VEL_LAYERS]; /* SiLU weight net */
+  NvfiLinear acc_net[NVFI_VEL_LAYERS]; /* ReLU twin net (PDE loss only) */
+  int32_t vel_gate;
+  float gate_lo[3], gate_hi[3]; /* velocity is zero outside [lo, hi] (normalised coords) */
+  /* eval-only empty-space mask (models/tensorf_model_utils.py:417-442); NULL = none */
+  const uint8_t* alpha_volume; /* (Gz, Gy, Gx) 0/1 */
+  int32_t alpha_grid[3];       /* (Gx, Gy, Gz) */
+  /* optional mask field (models/mask_field.py:34-83 as built at test_segm_render.py:75-80) */
+  int32_t mask_layers; /* 0 = none; else number of Linear layers incl. the head */
+  int32_t mask_dim;
+  NvfiLinear mask_net[NVFI_MAX_MASK_LAYERS];
+} NvfiField;
+
+/* Per-call render arguments: one time for all rays (a render call in the reference
+ * takes a scalar t, models/tensorf_keyframe.py:613-639). */
+typedef struct NvfiRenderArgs {
+  int64_t n_rays;
+  const float* rays_o;  /* (n_rays, 3) */
+  const float* rays_d;  /* (n_rays, 3), NOT normalised (models/camera.py:112-133) */
+  const float* jitter;  /* (n_rays) stratified offsets u in [0,1), or NULL (eval) */
+  int32_t ray_chunk;    /* reference chunk size (models/renderer.py:29); the
+                           inside-box predicate of sample_ray is evaluated per chunk */
+  const uint8_t* chunk_bg; /* (n_chunks) 1 = composite on white for this chunk, or NULL.
+                              Encodes `white_bg or (training and rand < .5)`
+                              (models/tensorf_keyframe.py:740). */
+  int32_t white_bg;     /* used when chunk_bg == NULL */
+  int32_t training;     /* 0: eval (alpha-mask skip active), 1: train */
+  float t;              /* query time */
+  float base_time;      /* keyframe time the samples are advected to (host: FP32 torch semantics) */
+  float t_norm_base;    /* normalize_time_coord(base_time) */
+  int32_t advect;       /* 0 when isclose(t, base) or !use_vel: no advection */
+} NvfiRenderArgs;
+
+/* Scratch + outputs of the forward pass; also what the backward pass re-reads. */
+typedef struct NvfiRenderBuffers {
+  /* per ray outputs */
+  float* rgb_map;   /* (n_rays, 3) */
+  float* depth_map; /* (n_rays) */
+  float* acc_map;   /* (n_rays) */
+  float* weights;   /* (n_rays, S) */
+  float* mask_map;  /* (n_rays, mask_dim or 3), zero-filled by the caller */
+  /* per sample scratch */
+  float* x_adv;     /* (n_rays, S, 3) advected normalised positions of valid samples */
+  uint8_t* valid;   /* (n_rays, S) */
+  float* rgb;       /* (n_rays, S, 3): written only where weights > weight_thres */
+  float* sigma;     /* (n_rays, S) density (saved for backward), may be NULL in eval */
+  /* small */
+  uint8_t* chunk_inside; /* (n_chunks) */
+  int32_t* counters;     /* >= 16 ints, zeroed by the callee */
+  int64_t* stats;        /* >= 4: [valid samples, advected samples, app samples, 0], or NULL */
+} NvfiRenderBuffers;
+
+/* Upstream gradients and gradient accumulators for the backward pass.  Plane
+ * gradients are accumulated in the packed (H, W, R) layout; nvfi_unpack_plane_grad
+ * converts back to NCHW.  All accumulators must be zero-initialised by the caller. */
+typedef struct NvfiRenderGrads {
+  const float* g_rgb;     /* (n_rays, 3) or NULL */
+  const float* g_depth;   /* (n_rays) or NULL */
+  const float* g_acc;     /* (n_rays) or NULL */
+  const float* g_weights; /* (n_rays, S) or NULL */
+  float* g_dplane_space[3];
+  float* g_dplane_time[3];
+  float* g_aplane_space[3];
+  float* g_aplane_time[3];
+  float* g_basis_mat;      /* packed (k_pad, n_pad) like NvfiLinear.wt */
+  float* g_render_w[3];    /* packed */
+  float* g_render_b[3];
+  float* g_vel_w[NVFI_VEL_LAYERS]; /* packed */
+  float* g_vel_b[NVFI_VEL_LAYERS];
+  float* g_x_adv;          /* scratch (n_rays, S, 3) */
+  float* g_sigma;          /* scratch (n_rays, S) */
+  float* partials;         /* scratch for per-CTA weight-gradient partial sums */
+  int64_t partials_bytes;
+} NvfiRenderGrads;
+
+/* ---- library info --------------------------------------------------------------- */
+int nvfi_abi_version(void);
+/* Bytes of `partials` scratch nvfi_render_backward needs for this device. */
+int64_t nvfi_backward_partials_bytes(void);
+
+/* ---- layout packing ----------------------------------------------------------------
+ * Replaces nothing in the reference (it reads NCHW through F.grid_sample,
+ * models/tensorf_keyframe.py:259-264); the packed layout makes one bilinear corner a
+ * single contiguous R-vector. */
+int nvfi_pack_plane(const float* src_nchw, float* dst_hwc, int r, int h, int w, void* stream);
+int nvfi_unpack_plane(const float* src_hwc, float* dst_nchw, int r, int h, int w, void* stream);
+/* nn.Linear (out,in) [+ bias] -> padded transposed (k_pad, n_pad) [+ (n_pad)] and back
+ * (gradients). */
+int nvfi_pack_linear(const float* w, const float* b, float* wt, float* bias_out, int out_dim,
+                     int in_dim, int k_pad, int n_pad, void* stream);
+int nvfi_unpack_linear(const float* wt, const float* bias_in, float* w, float* b, int out_dim,
+                       int in_dim, int k_pad, int n_pad, void* stream);
+
+/* ---- rays ----------------------------------------------------------------------------
+ * Camera.get_ray_bundle for selected pixels (models/camera.py:112-138):
+ * pixel_ids (n) int64 flat indices (row * W + col), or NULL for all H*W pixels. */
+int nvfi_raygen(const float* pose4x4, int h, int w, float focal, const int64_t* pixel_ids,
+                int64_t n, float* rays_o, float* rays_d, void* stream);
+
+/* ---- forward render -------------------------------------------------------------------
+ * TensorVMKeyframeTimeKplane.forward + render_pts over all chunks of a Renderer.forward
+ * call (models/renderer.py:22-56, models/tensorf_keyframe.py:613-755). */
+int nvfi_render_forward(const NvfiField* field, const NvfiRenderArgs* args,
+                        const NvfiRenderBuffers* buf, void* stream);
+
+/* Backward of nvfi_render_forward (autograd of the same reference functions). */
+int nvfi_render_backward(const NvfiField* field, const NvfiRenderArgs* args,
+                         const NvfiRenderBuffers* buf, const NvfiRenderGrads* grads,
+                         void* stream);
+
+/* Host-buffer variant of the eval render (the end-to-end entry point): rays and
+ * jitter come from HOST memory, rgb/depth/acc are copied back to HOST memory; the
+ * device scratch in `buf` is still caller-provided.  Synchronises `stream`. */
+int nvfi_render_forward_host(const NvfiField* field, const NvfiRenderArgs* args_devptrs_ignored,
+                             const float* rays_o_host, const float* rays_d_host,
+                             const float* jitter_host, float* dev_rays_o, float* dev_rays_d,
+                             float* dev_jitter, const NvfiRenderBuffers* buf,
+                             float* rgb_host, float* depth_host, float* acc_host, void* stream);
+
+/* ---- field queries (called directly by train_segm.py:138-166, models/nvfi.py:50-64) -- */
+/* integrate_pos (models/tensorf_keyframe.py:575-611): per-point t and base. x (n,3)
+ * normalised; out (n,3). */
+int nvfi_integrate_pos(const NvfiField* field, const float* x, const float* t, const float* base,
+                       int64_t n, float* out, int32_t* counters, void* stream);
+/* compute_densityfeature (models/tensorf_keyframe.py:233-272): xyzt (n,4) normalised. */
+int nvfi_density_feature(const NvfiField* field, const float* xyzt, int64_t n, float* feat,
+                         void* stream);
+/* compute_densityfeature followed by feature2density in one pass: sigma (n). */
+int nvfi_density_sigma(const NvfiField* field, const float* xyzt, int64_t n, float* sigma,
+                       void* stream);
+/* feature2density (models/tensorf_keyframe.py:312-325). */
+int nvfi_feature2density(const NvfiField* field, const float* feat, int64_t n, float* sigma,
+                         void* stream);
+/* compute_appfeature (models/tensorf_keyframe.py:274-310): out (n, app_dim). */
+int nvfi_app_feature(const NvfiField* field, const float* xyzt, int64_t n, float* feat,
+                     int32_t* counters, void* stream);
+/* VelBasis.forward / get_vel and the gated VelocityAABB(.Sur) (models/velocity_field.py):
+ * out (n, 6) = [v, a] when full != 0, else (n, 3) gated velocity. */
+int nvfi_velocity(const NvfiField* field, const float* xyzt, int64_t n, int32_t full, float* out,
+                  int32_t* counters, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVFI_B200_H */

@@ -1,0 +1,222 @@
+// C-ABI entry points (include/nvfi_b200.h): layout packing, ray generation and the
+// forward-render orchestration.  Every function validates its arguments, enqueues
+// kernels on the caller's stream and returns an error code; nothing here touches torch.
+#include "nvfi_common.cuh"
+
+extern "C" int nvfi_launch_sample_advect(const NvfiField*, const NvfiRenderArgs*,
+                                         const NvfiRenderBuffers*, cudaStream_t);
+extern "C" int nvfi_launch_march(const NvfiField*, const NvfiRenderArgs*, const NvfiRenderBuffers*,
+                                 cudaStream_t);
+extern "C" int nvfi_launch_appearance(const NvfiField*, const NvfiRenderArgs*,
+                                      const NvfiRenderBuffers*, cudaStream_t);
+extern "C" int nvfi_launch_composite(const NvfiField*, const NvfiRenderArgs*,
+                                     const NvfiRenderBuffers*, cudaStream_t);
+
+namespace nvfi {
+
+// (R, H*W) -> (H*W, R) tiled transpose through shared memory (both sides coalesced).
+__global__ void k_transpose(const float* __restrict__ src, float* __restrict__ dst, int rows,
+                            long long cols) {
+  __shared__ float tile[32][33];
+  const long long c0 = (long long)blockIdx.x * 32;
+  const int r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j;
+    const long long c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = src[(long long)r * cols + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long c = c0 + j;
+    const int r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[c * rows + r] = tile[threadIdx.x][j];
+  }
+}
+
+// nn.Linear (out,in) -> W^T zero-padded (k_pad, n_pad)
+__global__ void k_pack_linear(const float* __restrict__ w, const float* __restrict__ b,
+                              float* __restrict__ wt, float* __restrict__ bo, int out_dim,
+                              int in_dim, int k_pad, int n_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k_pad * n_pad) {
+    const int k = i / n_pad, n = i - k * n_pad;
+    wt[i] = (k < in_dim && n < out_dim) ? w[n * in_dim + k] : 0.f;
+  }
+  if (bo && i < n_pad) bo[i] = (b && i < out_dim) ? b[i] : 0.f;
+}
+
+__global__ void k_unpack_linear(const float* __restrict__ wt, const float* __restrict__ bi,
+                                float* __restrict__ w, float* __restrict__ b, int out_dim,
+                                int in_dim, int k_pad, int n_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < out_dim * in_dim) {
+    const int n = i / in_dim, k = i - n * in_dim;
+    w[i] = wt[k * n_pad + n];
+  }
+  if (b && bi && i < out_dim) b[i] = bi[i];
+}
+
+// Camera.get_ray_bundle (models/camera.py:112-138), per selected pixel.
+__global__ void k_raygen(const float* __restrict__ pose, int H, int W, float focal,
+                         const long long* __restrict__ pix, long long n, float* __restrict__ ro,
+                         float* __restrict__ rd) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long p = pix ? pix[i] : i;
+  const int row = (int)(p / W), col = (int)(p - (long long)row * W);
+  const float dx = __fdiv_rn(__fsub_rn((float)col, (float)W * 0.5f), focal);
+  const float dy = -__fdiv_rn(__fsub_rn((float)row, (float)H * 0.5f), focal);
+  const float dz = -1.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    // torch.sum(dirs[..., None, :] * pose[:3, :3], dim=-1): sequential sum of 3 products
+    const float s0 = __fmul_rn(dx, pose[a * 4 + 0]);
+    const float s1 = __fmul_rn(dy, pose[a * 4 + 1]);
+    const float s2 = __fmul_rn(dz, pose[a * 4 + 2]);
+    rd[i * 3 + a] = __fadd_rn(__fadd_rn(s0, s1), s2);
+    ro[i * 3 + a] = pose[a * 4 + 3];
+  }
+}
+
+}  // namespace nvfi
+
+using namespace nvfi;
+
+extern "C" int nvfi_abi_version(void) { return NVFI_ABI_VERSION; }
+
+static int launch_transpose(const float* src, float* dst, int rows, long long cols,
+                            cudaStream_t st) {
+  if (!src || !dst || rows <= 0 || cols <= 0) return NVFI_EINVAL;
+  dim3 block(32, 8);
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  k_transpose<<<grid, block, 0, st>>>(src, dst, rows, cols);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int nvfi_pack_plane(const float* src_nchw, float* dst_hwc, int r, int h, int w,
+                               void* stream) {
+  return launch_transpose(src_nchw, dst_hwc, r, (long long)h * w, (cudaStream_t)stream);
+}
+
+extern "C" int nvfi_unpack_plane(const float* src_hwc, float* dst_nchw, int r, int h, int w,
+                                 void* stream) {
+  // (H*W, R) -> (R, H*W): the same transpose with the roles of rows / cols exchanged
+  if (!src_hwc || !dst_nchw || r <= 0 || h <= 0 || w <= 0) return NVFI_EINVAL;
+  const long long hw = (long long)h * w;
+  if (hw > 0x7fffffffLL) return NVFI_EUNSUPPORTED;
+  dim3 block(32, 8);
+  dim3 grid((unsigned)((r + 31) / 32), (unsigned)((hw + 31) / 32));
+  k_transpose<<<grid, block, 0, (cudaStream_t)stream>>>(src_hwc, dst_nchw, (int)hw, r);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int nvfi_pack_linear(const float* w, const float* b, float* wt, float* bias_out,
+                                int out_dim, int in_dim, int k_pad, int n_pad, void* stream) {
+  if (!w || !wt || out_dim <= 0 || in_dim <= 0 || k_pad < in_dim || n_pad < out_dim)
+    return NVFI_EINVAL;
+  const int n = k_pad * n_pad > n_pad ? k_pad * n_pad : n_pad;
+  k_pack_linear<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, b, wt, bias_out, out_dim,
+                                                                    in_dim, k_pad, n_pad);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int nvfi_unpack_linear(const float* wt, const float* bias_in, float* w, float* b,
+                                  int out_dim, int in_dim, int k_pad, int n_pad, void* stream) {
+  if (!w || !wt || out_dim <= 0 || in_dim <= 0 || k_pad < in_dim || n_pad < out_dim)
+    return NVFI_EINVAL;
+  const int n = out_dim * in_dim;
+  k_unpack_linear<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(wt, bias_in, w, b, out_dim,
+                                                                      in_dim, k_pad, n_pad);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int nvfi_raygen(const float* pose4x4, int h, int w, float focal,
+                           const int64_t* pixel_ids, int64_t n, float* rays_o, float* rays_d,
+                           void* stream) {
+  if (!pose4x4 || !rays_o || !rays_d || h <= 0 || w <= 0 || n < 0) return NVFI_EINVAL;
+  if (n == 0) return NVFI_OK;
+  k_raygen<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      pose4x4, h, w, focal, reinterpret_cast<const long long*>(pixel_ids), n, rays_o, rays_d);
+  return (int)cudaGetLastError();
+}
+
+static int check_render_args(const NvfiField* F, const NvfiRenderArgs* A,
+                             const NvfiRenderBuffers* B) {
+  if (!F || !A || !B) return NVFI_EINVAL;
+  if (A->n_rays < 0 || A->ray_chunk <= 0) return NVFI_EINVAL;
+  if (A->n_rays == 0) return NVFI_OK;
+  if (!A->rays_o || !A->rays_d || !B->rgb_map || !B->depth_map || !B->acc_map || !B->weights ||
+      !B->x_adv || !B->valid || !B->rgb || !B->chunk_inside || !B->counters)
+    return NVFI_EINVAL;
+  if (A->training && !A->jitter) return NVFI_EINVAL;
+  if (F->n_samples <= 0 || F->n_samples > 4096) return NVFI_EUNSUPPORTED;
+  if (F->rd % 4 != 0 || F->rd <= 0 || F->rd > 64) return NVFI_EUNSUPPORTED;
+  if (F->mask_layers > 0 && !B->mask_map) return NVFI_EINVAL;
+  if (A->advect) {
+    if (!F->use_vel) return NVFI_EINVAL;
+    for (int l = 0; l < NVFI_VEL_LAYERS; ++l) {
+      const NvfiLinear& L = F->vel_net[l];
+      if (!L.wt || !L.bias) return NVFI_EINVAL;
+      if (l == 0 && (L.in_dim != NVFI_VEL_IN || L.k_pad != 32)) return NVFI_EUNSUPPORTED;
+      if (l > 0 && L.k_pad != 128) return NVFI_EUNSUPPORTED;
+      if (l < NVFI_VEL_LAYERS - 1 && L.n_pad != 128) return NVFI_EUNSUPPORTED;
+      if (l == NVFI_VEL_LAYERS - 1 && L.n_pad != 8) return NVFI_EUNSUPPORTED;
+    }
+  }
+  return NVFI_OK;
+}
+
+extern "C" int nvfi_render_forward(const NvfiField* F, const NvfiRenderArgs* A,
+                                   const NvfiRenderBuffers* B, void* stream) {
+  int rc = check_render_args(F, A, B);
+  if (rc != NVFI_OK) return rc;
+  if (A->n_rays == 0) return NVFI_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  NVFI_CUDA_OK(cudaMemsetAsync(B->counters, 0, 16 * sizeof(int32_t), st));
+  if (B->stats) NVFI_CUDA_OK(cudaMemsetAsync(B->stats, 0, 4 * sizeof(int64_t), st));
+  rc = nvfi_launch_sample_advect(F, A, B, st);
+  if (rc != NVFI_OK) return rc;
+  rc = nvfi_launch_march(F, A, B, st);
+  if (rc != NVFI_OK) return rc;
+  rc = nvfi_launch_appearance(F, A, B, st);
+  if (rc != NVFI_OK) return rc;
+  return nvfi_launch_composite(F, A, B, st);
+}
+
+extern "C" int nvfi_render_forward_host(const NvfiField* F, const NvfiRenderArgs* A_in,
+                                        const float* rays_o_host, const float* rays_d_host,
+                                        const float* jitter_host, float* dev_rays_o,
+                                        float* dev_rays_d, float* dev_jitter,
+                                        const NvfiRenderBuffers* B, float* rgb_host,
+                                        float* depth_host, float* acc_host, void* stream) {
+  if (!F || !A_in || !B || !rays_o_host || !rays_d_host || !dev_rays_o || !dev_rays_d)
+    return NVFI_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  NvfiRenderArgs A = *A_in;
+  const size_t n = (size_t)A.n_rays;
+  NVFI_CUDA_OK(cudaMemcpyAsync(dev_rays_o, rays_o_host, n * 3 * sizeof(float),
+                               cudaMemcpyHostToDevice, st));
+  NVFI_CUDA_OK(cudaMemcpyAsync(dev_rays_d, rays_d_host, n * 3 * sizeof(float),
+                               cudaMemcpyHostToDevice, st));
+  A.rays_o = dev_rays_o;
+  A.rays_d = dev_rays_d;
+  A.jitter = nullptr;
+  if (jitter_host) {
+    if (!dev_jitter) return NVFI_EINVAL;
+    NVFI_CUDA_OK(
+        cudaMemcpyAsync(dev_jitter, jitter_host, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    A.jitter = dev_jitter;
+  }
+  int rc = nvfi_render_forward(F, &A, B, st);
+  if (rc != NVFI_OK) return rc;
+  if (rgb_host)
+    NVFI_CUDA_OK(cudaMemcpyAsync(rgb_host, B->rgb_map, n * 3 * sizeof(float),
+                                 cudaMemcpyDeviceToHost, st));
+  if (depth_host)
+    NVFI_CUDA_OK(
+        cudaMemcpyAsync(depth_host, B->depth_map, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (acc_host)
+    NVFI_CUDA_OK(
+        cudaMemcpyAsync(acc_host, B->acc_map, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  return (int)cudaStreamSynchronize(st);
+}

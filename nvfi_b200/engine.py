@@ -1,0 +1,456 @@
+"""Host-side engine: binds a field module's parameters to the C-ABI structs, keeps the
+packed (channels-last / transposed) device copies fresh, and drives the CUDA library.
+
+PyTorch is plumbing here: device memory, streams and autograd bookkeeping.  All hot-path
+arithmetic happens in ``libnvfi_b200.so``; there is no eager fallback.
+
+Reference behaviour mirrored (host-side scalar logic only):
+  * keyframe snap / isclose / time normalisation: models/tensorf_keyframe.py:646-654, 683,
+    501-506 — evaluated with torch CPU FP32 ops on a 1-element tensor so the result is
+    bit-identical to the reference's per-sample tensors (a render call has ONE time);
+  * stratified jitter and random-background draws come from the CPU generator in the same
+    order as the reference's chunk loop (models/tensorf_base.py:302-306,
+    models/tensorf_keyframe.py:740, models/renderer.py:29-42).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+MAT_MODE_SPACE = ((0, 1), (0, 2), (1, 2))
+MAT_MODE_TIME = ((2, 3), (1, 3), (0, 3))
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def _f32(x) -> float:
+    """Round a python number to FP32 the way torch does when it meets a float tensor."""
+    return float(torch.tensor(float(x), dtype=torch.float32))
+
+
+class _Tracked:
+    """Remembers (data_ptr, version) of source tensors to know when a packed copy is stale."""
+
+    def __init__(self):
+        self.key = None
+
+    def stale(self, tensors: Sequence[Optional[torch.Tensor]]) -> bool:
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) if t is not None else None
+                    for t in tensors)
+        if key != self.key:
+            self.key = key
+            return True
+        return False
+
+
+class PackedLinear:
+    """nn.Linear weight (out,in)[, bias] -> zero-padded W^T (k_pad, n_pad) [+ (n_pad)]."""
+
+    def __init__(self, out_dim: int, in_dim: int, device, hidden: bool, has_bias: bool = True):
+        self.out_dim, self.in_dim = out_dim, in_dim
+        self.k_pad = _round_up(in_dim, 32)
+        self.n_pad = 128 if hidden else _round_up(out_dim, 4)
+        if hidden and out_dim != 128:
+            raise RuntimeError(f"nvfi_b200: hidden width {out_dim} unsupported (kernels are built for 128)")
+        self.wt = torch.zeros(self.k_pad, self.n_pad, device=device, dtype=torch.float32)
+        self.bias = torch.zeros(self.n_pad, device=device, dtype=torch.float32) if has_bias else None
+        self.track = _Tracked()
+
+    def sync(self, w: torch.Tensor, b: Optional[torch.Tensor]):
+        if not self.track.stale((w, b)):
+            return
+        lib = L.load()
+        wd = w.detach().contiguous()
+        bd = b.detach().contiguous() if b is not None else None
+        L.check(lib.nvfi_pack_linear(wd.data_ptr(), _ptr(bd), self.wt.data_ptr(), _ptr(self.bias),
+                                     self.out_dim, self.in_dim, self.k_pad, self.n_pad, _stream()),
+                "pack_linear")
+
+    def fill(self, s: L.NvfiLinear):
+        s.wt = self.wt.data_ptr()
+        s.bias = _ptr(self.bias)
+        s.in_dim, s.out_dim, s.k_pad, s.n_pad = self.in_dim, self.out_dim, self.k_pad, self.n_pad
+
+    def unpack_grad(self, g_wt: torch.Tensor, g_b: Optional[torch.Tensor], want_bias: bool):
+        lib = L.load()
+        gw = torch.empty(self.out_dim, self.in_dim, device=g_wt.device, dtype=torch.float32)
+        gb = torch.empty(self.out_dim, device=g_wt.device, dtype=torch.float32) if want_bias else None
+        L.check(lib.nvfi_unpack_linear(g_wt.data_ptr(), _ptr(g_b), gw.data_ptr(), _ptr(gb),
+                                       self.out_dim, self.in_dim, self.k_pad, self.n_pad, _stream()),
+                "unpack_linear")
+        return gw, gb
+
+
+class PackedPlane:
+    """(1, R, H, W) parameter -> packed (H, W, R)."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+        self.track = _Tracked()
+        self.shape = None
+
+    def sync(self, p: torch.Tensor):
+        if not self.track.stale((p,)):
+            return
+        _, R, H, W = p.shape
+        if self.buf is None or self.shape != (R, H, W):
+            self.buf = torch.empty(H, W, R, device=p.device, dtype=torch.float32)
+            self.shape = (R, H, W)
+        src = p.detach().contiguous()
+        L.check(L.load().nvfi_pack_plane(src.data_ptr(), self.buf.data_ptr(), R, H, W, _stream()),
+                "pack_plane")
+
+    def unpack_grad(self, g: torch.Tensor) -> torch.Tensor:
+        R, H, W = self.shape
+        out = torch.empty(1, R, H, W, device=g.device, dtype=torch.float32)
+        L.check(L.load().nvfi_unpack_plane(g.data_ptr(), out.data_ptr(), R, H, W, _stream()),
+                "unpack_plane")
+        return out
+
+
+def vel_linears(vel_net) -> List[Tuple[torch.Tensor, torch.Tensor]]:
+    """(weight, bias) of the 6 Linear layers of VelBasis.weight_net / a_weight_net
+    (models/velocity_field.py:58-67: index 1, then [3..7][0])."""
+    seq = vel_net
+    out = [(seq[1].weight, seq[1].bias)]
+    for i in range(3, 8):
+        out.append((seq[i][0].weight, seq[i][0].bias))
+    return out
+
+
+class FieldBinding:
+    """Device-side view of one field module (``nvfi_b200.models.TensorVMKeyframeTimeKplane``
+    or anything exposing the same attributes)."""
+
+    def __init__(self, field):
+        self.field = field
+        self.s = L.NvfiField()
+        self.planes = {k: [PackedPlane() for _ in range(3)]
+                       for k in ("density_plane_space", "density_plane_time",
+                                 "app_plane_space", "app_plane_time")}
+        self.basis: Optional[PackedLinear] = None
+        self.render: Optional[List[PackedLinear]] = None
+        self.vel: Optional[List[PackedLinear]] = None
+        self.acc: Optional[List[PackedLinear]] = None
+        self.mask: Optional[List[PackedLinear]] = None
+        self.mask_key = None
+        self.alpha_track = _Tracked()
+        self.alpha_u8: Optional[torch.Tensor] = None
+
+    # -- helpers --------------------------------------------------------------------------
+    def _device(self):
+        return self.field.density_plane_space[0].device
+
+    def sync(self) -> L.NvfiField:
+        """Refresh packed buffers whose sources changed and refill the C struct."""
+        f, s = self.field, self.s
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("nvfi_b200: the field must live on a CUDA device (no CPU fallback)")
+        aabb = f.aabb.detach().float().cpu()
+        inv = f.invaabbSize.detach().float().cpu()
+        grid = [int(g) for g in (f.gridSize.tolist() if torch.is_tensor(f.gridSize) else f.gridSize)]
+        K = int(f.num_keyframes)
+        for a in range(3):
+            s.aabb_min[a] = float(aabb[0, a])
+            s.aabb_max[a] = float(aabb[1, a])
+            s.inv_aabb[a] = float(inv[a])
+            s.grid[a] = grid[a]
+        s.num_keyframes = K
+        s.tmax = _f32(f.tmax)
+        s.time_scale = _f32(f.tmax / (K - 1) if K > 1 else 1)
+        s.dt_max = _f32(0.5 * f.tmax / (K - 1) if K > 1 else 1)
+        s.near, s.far = _f32(f.near_far[0]), _f32(f.near_far[1])
+        s.step_size = float(f.stepSize.detach().float().cpu()) if torch.is_tensor(f.stepSize) else _f32(f.stepSize)
+        s.n_samples = int(f.nSamples)
+        s.density_shift = _f32(f.density_shift)
+        s.distance_scale = _f32(f.distance_scale)
+        s.weight_thres = _f32(f.rayMarch_weight_thres)
+        s.fea2dense_act = {"softplus": L.ACT_SOFTPLUS, "relu": L.ACT_RELU, "relu_abs": L.ACT_RELU_ABS}[f.fea2denseAct]
+        if f.densityMode != "Density":
+            raise RuntimeError(f"nvfi_b200: densityMode {f.densityMode!r} unsupported (configs use 'Density')")
+        if f.shadingMode == "MLP_PE":
+            s.shading_mode = L.SHADING_MLP_PE
+        elif f.shadingMode == "SH":
+            s.shading_mode = L.SHADING_SH
+        else:
+            raise RuntimeError(f"nvfi_b200: shadingMode {f.shadingMode!r} unsupported (MLP_PE, SH)")
+        s.pos_pe, s.view_pe = int(f.pos_pe), int(f.view_pe)
+        s.rd = int(f.density_plane_space[0].shape[1])
+        s.ra = int(f.app_plane_space[0].shape[1])
+        s.app_dim = int(f.app_dim)
+        for k in range(3):
+            for name, dst in (("density_plane_space", s.dplane_space), ("density_plane_time", s.dplane_time),
+                              ("app_plane_space", s.aplane_space), ("app_plane_time", s.aplane_time)):
+                pp = self.planes[name][k]
+                pp.sync(getattr(f, name)[k])
+                dst[k] = pp.buf.data_ptr()
+        # basis_mat
+        if self.basis is None or self.basis.out_dim != s.app_dim or self.basis.in_dim != s.ra:
+            self.basis = PackedLinear(s.app_dim, s.ra, dev, hidden=False, has_bias=False)
+        self.basis.sync(f.basis_mat.weight, None)
+        self.basis.fill(s.basis_mat)
+        # render MLP
+        if s.shading_mode == L.SHADING_MLP_PE:
+            mlp = f.renderModule.mlp
+            lins = [mlp[0], mlp[2], mlp[4]]
+            if self.render is None or self.render[0].in_dim != lins[0].in_features:
+                self.render = [PackedLinear(l.out_features, l.in_features, dev, hidden=(i < 2))
+                               for i, l in enumerate(lins)]
+            for i, l in enumerate(lins):
+                self.render[i].sync(l.weight, l.bias)
+                self.render[i].fill(s.render_mlp[i])
+        # velocity nets
+        s.use_vel = 1 if f.use_vel else 0
+        if f.use_vel:
+            if self.vel is None:
+                dims = [(128, 28)] + [(128, 128)] * 4 + [(6, 128)]
+                self.vel = [PackedLinear(o, i, dev, hidden=(j < 5)) for j, (o, i) in enumerate(dims)]
+                self.acc = [PackedLinear(o, i, dev, hidden=(j < 5)) for j, (o, i) in enumerate(dims)]
+            for j, (w, b) in enumerate(vel_linears(f.vel_net.weight_net)):
+                self.vel[j].sync(w, b)
+                self.vel[j].fill(s.vel_net[j])
+            for j, (w, b) in enumerate(vel_linears(f.vel_net.a_weight_net)):
+                self.acc[j].sync(w, b)
+                self.acc[j].fill(s.acc_net[j])
+            lo, hi = f.vel_gate_bounds()
+            s.vel_gate = L.GATE_SUR if f.vel_gate_kind() == "sur" else L.GATE_AABB
+            for a in range(3):
+                s.gate_lo[a], s.gate_hi[a] = lo[a], hi[a]
+        # alpha mask
+        am = getattr(f, "alphaMask", None)
+        if am is not None:
+            vol = am.alpha_volume
+            if self.alpha_track.stale((vol,)):
+                self.alpha_u8 = (vol.detach().reshape(vol.shape[-3:]) > 0).to(torch.uint8).contiguous()
+            s.alpha_volume = self.alpha_u8.data_ptr()
+            s.alpha_grid[0], s.alpha_grid[1], s.alpha_grid[2] = (int(vol.shape[-1]), int(vol.shape[-2]),
+                                                                 int(vol.shape[-3]))
+        else:
+            s.alpha_volume = None
+            self.alpha_track.key = None
+        # mask field
+        mf = getattr(f, "mask_field", None)
+        if mf is not None:
+            if getattr(mf, "point_embed", None) is not None or len(getattr(mf, "skips", [])) > 0 and any(
+                    sk < len(mf.point_fc) for sk in mf.skips):
+                raise RuntimeError("nvfi_b200: MaskField with point_embed / skips is unsupported")
+            lins = list(mf.point_fc) + [mf.mask_fc]
+            key = tuple((l.out_features, l.in_features) for l in lins)
+            if self.mask is None or self.mask_key != key:
+                self.mask = [PackedLinear(l.out_features, l.in_features, dev, hidden=(i < len(lins) - 1))
+                             for i, l in enumerate(lins)]
+                self.mask_key = key
+            for i, l in enumerate(lins):
+                self.mask[i].sync(l.weight, l.bias)
+                self.mask[i].fill(s.mask_net[i])
+            s.mask_layers = len(lins)
+            s.mask_dim = int(mf.mask_dim)
+        else:
+            s.mask_layers = 0
+            s.mask_dim = 3
+        return s
+
+
+# ------------------------------------------------------------------------------------------
+# per-call scalar logic
+# ------------------------------------------------------------------------------------------
+def time_plan(field, t, transfer_vel: bool) -> Tuple[float, float, float, bool]:
+    """(t, base_time, t_norm_of_eval_time, advect) with the reference's FP32 tensor semantics
+    (models/tensorf_keyframe.py:646-654, 683-699, 501-506)."""
+    tt = torch.ones(1, dtype=torch.float32) * (t.detach().cpu() if torch.is_tensor(t) else t)
+    K = int(field.num_keyframes)
+    tsf = field.tmax / (K - 1) if K > 1 else 1
+    if transfer_vel:
+        base = torch.zeros_like(tt)
+    else:
+        base = torch.round((tt / tsf).clamp(0.0, K - 1)) * tsf
+
+    def norm_t(x):
+        if K == 1 or field.tmax == 0:
+            return x * 0
+        return x * 2 / field.tmax - 1
+
+    if field.use_vel:
+        key = bool(torch.isclose(tt, base))
+        return float(tt), float(base), float(norm_t(base)), not key
+    return float(tt), float(base), float(norm_t(tt)), False
+
+
+class RenderOutputs:
+    __slots__ = ("rgb_map", "depth_map", "acc_map", "weights", "mask_map", "x_adv", "valid", "rgb",
+                 "sigma", "chunk_inside", "counters", "stats", "args", "keep")
+
+
+def render_forward(binding: FieldBinding, rays_o: torch.Tensor, rays_d: torch.Tensor, t, *,
+                   white_bg: bool, training: bool, jitter: Optional[torch.Tensor] = None,
+                   chunk_bg: Optional[torch.Tensor] = None, transfer_vel: bool = False,
+                   ray_chunk: int = 2048, save_sigma: bool = False,
+                   want_stats: bool = False) -> RenderOutputs:
+    """One nvfi_render_forward call over all rays (all reference chunks at once)."""
+    lib = L.load()
+    s = binding.sync()
+    dev = rays_o.device
+    if dev.type != "cuda":
+        raise RuntimeError("nvfi_b200: rays must be CUDA tensors (no CPU fallback)")
+    rays_o = rays_o.detach().reshape(-1, 3).contiguous().float()
+    rays_d = rays_d.detach().reshape(-1, 3).contiguous().float()
+    n = rays_o.shape[0]
+    S = int(s.n_samples)
+    tt, base, tnb, advect = time_plan(binding.field, t, transfer_vel)
+    n_chunks = max(1, (n + ray_chunk - 1) // ray_chunk)
+
+    o = RenderOutputs()
+    f32 = dict(device=dev, dtype=torch.float32)
+    o.rgb_map = torch.empty(n, 3, **f32)
+    o.depth_map = torch.empty(n, **f32)
+    o.acc_map = torch.empty(n, **f32)
+    o.weights = torch.empty(n, S, **f32)
+    o.mask_map = torch.zeros(n, int(s.mask_dim) if s.mask_layers > 0 else 3, **f32)
+    o.x_adv = torch.empty(n, S, 3, **f32)
+    o.valid = torch.empty(n, S, device=dev, dtype=torch.uint8)
+    o.rgb = torch.empty(n, S, 3, **f32)
+    o.sigma = torch.empty(n, S, **f32) if save_sigma else None
+    o.chunk_inside = torch.empty(n_chunks, device=dev, dtype=torch.uint8)
+    o.counters = torch.empty(16, device=dev, dtype=torch.int32)
+    o.stats = torch.empty(4, device=dev, dtype=torch.int64) if want_stats else None
+
+    a = L.NvfiRenderArgs()
+    a.n_rays = n
+    a.rays_o, a.rays_d = rays_o.data_ptr(), rays_d.data_ptr()
+    if training:
+        if jitter is None:
+            raise RuntimeError("nvfi_b200: training render needs the per-ray jitter tensor")
+        jitter = jitter.detach().reshape(-1).contiguous().float()
+        if jitter.device != dev:
+            jitter = jitter.to(dev, non_blocking=True)
+        if jitter.numel() != n:
+            raise RuntimeError("nvfi_b200: jitter must have one entry per ray")
+        a.jitter = jitter.data_ptr()
+    else:
+        a.jitter = None
+    a.ray_chunk = int(ray_chunk)
+    if chunk_bg is not None:
+        chunk_bg = chunk_bg.to(device=dev, dtype=torch.uint8).contiguous()
+        if chunk_bg.numel() != n_chunks:
+            raise RuntimeError("nvfi_b200: chunk_bg must have one entry per chunk")
+        a.chunk_bg = chunk_bg.data_ptr()
+    else:
+        a.chunk_bg = None
+    a.white_bg = 1 if white_bg else 0
+    a.training = 1 if training else 0
+    a.t, a.base_time, a.t_norm_base, a.advect = tt, base, tnb, 1 if advect else 0
+
+    b = L.NvfiRenderBuffers()
+    b.rgb_map, b.depth_map, b.acc_map = o.rgb_map.data_ptr(), o.depth_map.data_ptr(), o.acc_map.data_ptr()
+    b.weights, b.mask_map = o.weights.data_ptr(), o.mask_map.data_ptr()
+    b.x_adv, b.valid, b.rgb = o.x_adv.data_ptr(), o.valid.data_ptr(), o.rgb.data_ptr()
+    b.sigma = _ptr(o.sigma)
+    b.chunk_inside, b.counters, b.stats = o.chunk_inside.data_ptr(), o.counters.data_ptr(), _ptr(o.stats)
+    L.check(lib.nvfi_render_forward(C.byref(s), C.byref(a), C.byref(b), _stream()), "render_forward")
+    o.args = (a, b)
+    o.keep = (rays_o, rays_d, jitter, chunk_bg)
+    return o
+
+
+# ------------------------------------------------------------------------------------------
+# field queries
+# ------------------------------------------------------------------------------------------
+def _counters(dev):
+    return torch.empty(16, device=dev, dtype=torch.int32)
+
+
+def integrate_pos(binding: FieldBinding, x: torch.Tensor, t: torch.Tensor, base: torch.Tensor) -> torch.Tensor:
+    s = binding.sync()
+    x = x.detach().reshape(-1, 3).contiguous().float()
+    n = x.shape[0]
+    t = t.detach().reshape(-1).contiguous().float()
+    base = base.detach().reshape(-1).contiguous().float()
+    out = torch.empty_like(x)
+    cnt = _counters(x.device)
+    L.check(L.load().nvfi_integrate_pos(C.byref(s), x.data_ptr(), t.data_ptr(), base.data_ptr(), n,
+                                        out.data_ptr(), cnt.data_ptr(), _stream()), "integrate_pos")
+    return out
+
+
+def density_feature(binding: FieldBinding, xyzt: torch.Tensor) -> torch.Tensor:
+    s = binding.sync()
+    xyzt = xyzt.detach().reshape(-1, 4).contiguous().float()
+    n = xyzt.shape[0]
+    out = torch.empty(n, 1, device=xyzt.device, dtype=torch.float32)
+    L.check(L.load().nvfi_density_feature(C.byref(s), xyzt.data_ptr(), n, out.data_ptr(), _stream()),
+            "density_feature")
+    return out
+
+
+def density_sigma(binding: FieldBinding, xyzt: torch.Tensor) -> torch.Tensor:
+    s = binding.sync()
+    xyzt = xyzt.detach().reshape(-1, 4).contiguous().float()
+    n = xyzt.shape[0]
+    out = torch.empty(n, device=xyzt.device, dtype=torch.float32)
+    L.check(L.load().nvfi_density_sigma(C.byref(s), xyzt.data_ptr(), n, out.data_ptr(), _stream()),
+            "density_sigma")
+    return out
+
+
+def feature2density(binding: FieldBinding, feat: torch.Tensor) -> torch.Tensor:
+    s = binding.sync()
+    f = feat.detach().contiguous().float()
+    out = torch.empty_like(f)
+    L.check(L.load().nvfi_feature2density(C.byref(s), f.data_ptr(), f.numel(), out.data_ptr(), _stream()),
+            "feature2density")
+    return out
+
+
+def app_feature(binding: FieldBinding, xyzt: torch.Tensor) -> torch.Tensor:
+    s = binding.sync()
+    xyzt = xyzt.detach().reshape(-1, 4).contiguous().float()
+    n = xyzt.shape[0]
+    out = torch.empty(n, int(s.app_dim), device=xyzt.device, dtype=torch.float32)
+    cnt = _counters(xyzt.device)
+    L.check(L.load().nvfi_app_feature(C.byref(s), xyzt.data_ptr(), n, out.data_ptr(), cnt.data_ptr(),
+                                      _stream()), "app_feature")
+    return out
+
+
+def velocity(binding: FieldBinding, xyzt: torch.Tensor, full: bool) -> torch.Tensor:
+    s = binding.sync()
+    xyzt = xyzt.detach().reshape(-1, 4).contiguous().float()
+    n = xyzt.shape[0]
+    out = torch.empty(n, 6 if full else 3, device=xyzt.device, dtype=torch.float32)
+    cnt = _counters(xyzt.device)
+    L.check(L.load().nvfi_velocity(C.byref(s), xyzt.data_ptr(), n, 1 if full else 0, out.data_ptr(),
+                                   cnt.data_ptr(), _stream()), "velocity")
+    return out
+
+
+def raygen(pose: torch.Tensor, H: int, W: int, focal: float,
+           pixel_ids: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Camera.get_ray_bundle for selected flat pixel ids (or all pixels), on the device."""
+    pose = pose.detach().contiguous().float()
+    dev = pose.device
+    if pixel_ids is not None:
+        pixel_ids = pixel_ids.to(device=dev, dtype=torch.int64).contiguous()
+        n = pixel_ids.numel()
+    else:
+        n = H * W
+    ro = torch.empty(n, 3, device=dev, dtype=torch.float32)
+    rd = torch.empty(n, 3, device=dev, dtype=torch.float32)
+    L.check(L.load().nvfi_raygen(pose.data_ptr(), H, W, _f32(focal), _ptr(pixel_ids), n, ro.data_ptr(),
+                                 rd.data_ptr(), _stream()), "raygen")
+    return ro, rd

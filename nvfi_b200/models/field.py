@@ -1,0 +1,378 @@
+"""Keyframe k-planes field: parameter container + host orchestration.
+
+Mirrors the public surface of the reference's ``TensorVMKeyframeTimeKplane``
+(models/tensorf_keyframe.py:37-755) and its ``TensorBase`` parent
+(models/tensorf_base.py:133-351) — same constructor, attributes, parameter names and
+method signatures — while every hot-path computation is a call into the CUDA library
+through ``nvfi_b200.engine``.  What stays in torch here is host-side bookkeeping and the
+per-step regularisers that read each plane once.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import engine
+from ..autograd import render_with_grad
+from .velocity import VelBasis, VelocityAABB, VelocityAABBSur
+
+MAT_MODE_SPACE = [[0, 1], [0, 2], [1, 2]]
+MAT_MODE_TIME = [[2, 3], [1, 3], [0, 3]]
+
+
+class AlphaGridMask(nn.Module):
+    """Binary occupancy volume for eval-time empty-space skipping
+    (models/tensorf_model_utils.py:417-442).  The render kernels read it directly."""
+
+    def __init__(self, device, aabb, alpha_volume):
+        super().__init__()
+        self.opt_group = "color"
+        self.device = device
+        self.register_buffer("alpha_aabb", aabb.to(device))
+        self.register_buffer("alpha_volume", alpha_volume.view(1, 1, *alpha_volume.shape[-3:]))
+        self.aabbSize = self.alpha_aabb[1] - self.alpha_aabb[0]
+        self.invgridSize = 1.0 / self.aabbSize * 2
+        self.gridSize = torch.LongTensor([alpha_volume.shape[-1], alpha_volume.shape[-2],
+                                          alpha_volume.shape[-3]]).to(device)
+
+    def sample_alpha(self, xyz_sampled):
+        return F.grid_sample(self.alpha_volume, xyz_sampled.view(1, -1, 1, 1, 3),
+                             align_corners=True).view(-1)
+
+    def normalize_coord(self, xyz_sampled):
+        return (xyz_sampled - self.alpha_aabb[0]) * self.invgridSize - 1
+
+
+class MLPRender_PE(nn.Module):
+    """Parameter container of the configured appearance decoder
+    (models/tensorf_base.py:67-98): [feat, view, pts, PE(pts), PE(view)] -> 128 -> 128 -> 3.
+    Evaluated inside the appearance kernel."""
+
+    def __init__(self, inChanel, viewpe=6, pospe=6, featureC=128):
+        super().__init__()
+        self.opt_group = "color_impl"
+        self.in_mlpC = (3 + 2 * viewpe * 3) + (3 + 2 * pospe * 3) + inChanel
+        self.viewpe, self.pospe = viewpe, pospe
+        self.mlp = nn.Sequential(nn.Linear(self.in_mlpC, featureC), nn.ReLU(inplace=True),
+                                 nn.Linear(featureC, featureC), nn.ReLU(inplace=True),
+                                 nn.Linear(featureC, 3))
+        nn.init.constant_(self.mlp[-1].bias, 0)
+
+
+def SHRender(*_a, **_k):
+    raise RuntimeError("SHRender is evaluated inside the appearance kernel")
+
+
+class TensorVMKeyframeTimeKplane(nn.Module):
+    def __init__(self, aabb, gridSize, device, near_far, cfg):
+        super().__init__()
+        self.matModeSpace, self.matModeTime = MAT_MODE_SPACE, MAT_MODE_TIME
+        self.cfg = cfg
+        self.device = device
+        self.num_keyframes = cfg.num_keyframes
+        self.tmax = cfg.tmax
+        self.dt = 0.51
+        self.time_scale_factor = self.tmax / (self.num_keyframes - 1) if self.num_keyframes > 1 else 1
+        self.densityMode = cfg.densityMode
+        if self.densityMode != "Density":
+            raise NotImplementedError("nvfi_b200 supports densityMode == 'Density' (all shipped configs)")
+        self.data_dim_density = 1
+
+        self.register_buffer("aabb", aabb.to(device))
+        self.step_ratio = cfg.step_ratio
+        self.max_n_samples = cfg.max_n_samples
+        self.near_far = near_far
+        self.density_n_comp = cfg.density_n_comp
+        self.app_n_comp = cfg.appearance_n_comp
+        self.app_dim = cfg.app_dim
+        self.density_shift = cfg.density_shift
+        self.distance_scale = cfg.distance_scale
+        self.alphaMask = None
+        self.alphaMask_thres = cfg.alphaMask_thres
+        self.rayMarch_weight_thres = cfg.rayMarch_weight_thres
+        self.fea2denseAct = cfg.fea2denseAct
+        self.update_stepSize(gridSize, verbose=False)
+
+        # parameters, created in the reference's order so a seeded run draws the same values
+        scale_d = 0.8 if self.fea2denseAct == "softplus" else 0.5
+        self.density_plane_space, self.density_plane_time = self._init_planes(
+            self.density_n_comp, gridSize, self.num_keyframes, scale_d, device)
+        self.app_plane_space, self.app_plane_time = self._init_planes(
+            self.app_n_comp, gridSize, self.num_keyframes, 0.1, device)
+        self.basis_mat = nn.Linear(self.app_n_comp[0], self.app_dim, bias=False).to(device)
+        self.basis_mat_density = nn.Linear(self.density_n_comp[0], self.data_dim_density, bias=False).to(device)
+
+        self.shadingMode = cfg.shadingMode
+        self.pos_pe, self.view_pe, self.fea_pe, self.featureC = cfg.pos_pe, cfg.view_pe, cfg.fea_pe, cfg.featureC
+        if self.shadingMode == "MLP_PE":
+            self.renderModule = MLPRender_PE(self.app_dim, self.view_pe, self.pos_pe, self.featureC).to(device)
+        elif self.shadingMode == "SH":
+            self.renderModule = SHRender
+        else:
+            raise NotImplementedError(f"nvfi_b200: shadingMode {self.shadingMode!r} (supported: MLP_PE, SH)")
+
+        self.use_vel = cfg.use_vel
+        if self.use_vel:
+            self.vel_net = VelBasis()
+            eps = cfg.eps if "eps" in cfg else 0.03
+            if all(k in cfg for k in ("sur_x", "sur_y", "sur_z")):
+                sur = torch.stack([torch.tensor(cfg[k]) for k in ("sur_x", "sur_y", "sur_z")], dim=-1).to(device)
+                self.vel = VelocityAABBSur(self.vel_net, self.aabb, sur)
+            else:
+                self.vel = VelocityAABB(self.vel_net, eps)
+        self.mask_field = None
+        self.contract_ray = bool(cfg.contract_ray) if "contract_ray" in cfg else False
+        if self.contract_ray:
+            raise NotImplementedError("nvfi_b200: contract_ray is config-dead in the reference and unsupported")
+        self._binding = engine.FieldBinding(self)
+        if self.use_vel:
+            self.vel_net._binding = self._binding
+
+    # ---------------------------------------------------------------- construction helpers
+    @staticmethod
+    def _init_planes(n_component, gridSize, numFrames, scale, device):
+        """Space planes scale*U(0.1,0.5), time planes 1 (models/tensorf_keyframe.py:137-186);
+        the resulting leaves are plain Parameters."""
+        space, time = [], []
+        for i in range(3):
+            m0, m1 = MAT_MODE_SPACE[i]
+            n0, _ = MAT_MODE_TIME[i]
+            p = torch.empty(1, n_component[i], gridSize[m1], gridSize[m0])
+            nn.init.uniform_(p, a=0.1, b=0.5)
+            space.append(nn.Parameter(scale * p))
+            time.append(nn.Parameter(torch.ones(1, n_component[i], numFrames, gridSize[n0])))
+        return nn.ParameterList(space).to(device), nn.ParameterList(time).to(device)
+
+    def update_stepSize(self, gridSize, verbose=True):
+        """models/tensorf_base.py:214-227."""
+        self.aabbSize = self.aabb[1] - self.aabb[0]
+        self.invaabbSize = 2.0 / self.aabbSize
+        self.gridSize = torch.LongTensor(list(gridSize)).to(self.aabb.device)
+        self.units = self.aabbSize / (self.gridSize - 1)
+        self.stepSize = torch.mean(self.units) * self.step_ratio
+        self.aabbDiag = torch.sqrt(torch.sum(torch.square(self.aabbSize)))
+        self.nSamples = min(self.max_n_samples, int((self.aabbDiag / self.stepSize).item()) + 1)
+        if verbose:
+            print("grid size", list(gridSize), "step", float(self.stepSize), "samples", self.nSamples)
+
+    def get_kwargs(self):
+        """models/tensorf_base.py:247-268."""
+        kw = {"aabb": self.aabb,
+              "gridSize": self.gridSize.tolist() if not isinstance(self.gridSize, list) else self.gridSize,
+              "density_n_comp": self.density_n_comp, "appearance_n_comp": self.app_n_comp,
+              "app_dim": self.app_dim, "density_shift": self.density_shift,
+              "alphaMask_thres": self.alphaMask_thres, "fea2denseAct": self.fea2denseAct,
+              "near_far": self.near_far, "step_ratio": self.step_ratio, "shadingMode": self.shadingMode,
+              "pos_pe": self.pos_pe, "view_pe": self.view_pe, "fea_pe": self.fea_pe,
+              "featureC": self.featureC, "num_keyframes": self.num_keyframes}
+        if self.alphaMask is not None:
+            kw |= {"alphaMask_grid": self.alphaMask.gridSize}
+        return kw
+
+    def get_optparam_groups(self, lr_init_spatialxyz=0.02, lr_init_network=0.001):
+        """models/tensorf_keyframe.py:539-550."""
+        groups = [{"params": self.density_plane_space, "lr": lr_init_spatialxyz},
+                  {"params": self.density_plane_time, "lr": lr_init_spatialxyz},
+                  {"params": self.app_plane_space, "lr": lr_init_spatialxyz},
+                  {"params": self.app_plane_time, "lr": lr_init_spatialxyz},
+                  {"params": self.basis_mat.parameters(), "lr": lr_init_network},
+                  {"params": self.basis_mat_density.parameters(), "lr": lr_init_network}]
+        if isinstance(self.renderModule, nn.Module):
+            groups += [{"params": self.renderModule.parameters(), "lr": lr_init_network}]
+        if self.use_vel:
+            groups += [{"params": self.vel.parameters(), "lr": lr_init_network}]
+        return groups
+
+    # ---------------------------------------------------------------- engine hooks
+    def vel_gate_kind(self):
+        return self.vel.gate()[0]
+
+    def vel_gate_bounds(self):
+        _, lo, hi = self.vel.gate()
+        return lo, hi
+
+    @property
+    def binding(self) -> engine.FieldBinding:
+        return self._binding
+
+    # ---------------------------------------------------------------- coordinates
+    def normalize_coord(self, xyz_sampled):
+        return (xyz_sampled - self.aabb[0]) * self.invaabbSize - 1
+
+    def normalize_time_coord(self, time):
+        if self.num_keyframes == 1 or self.tmax == 0:
+            return time * 0
+        return time * 2 / self.tmax - 1
+
+    # ---------------------------------------------------------------- field queries (no grad)
+    def compute_densityfeature(self, xyz_sampled):
+        """(V,4) normalised xyzt -> (V,1)  (models/tensorf_keyframe.py:233-272)."""
+        return engine.density_feature(self._binding, xyz_sampled)
+
+    def compute_appfeature(self, xyz_sampled):
+        """(A,4) -> (A, app_dim)  (models/tensorf_keyframe.py:274-310)."""
+        return engine.app_feature(self._binding, xyz_sampled)
+
+    def feature2density(self, density_features, x: Optional[Dict] = None):
+        """models/tensorf_keyframe.py:312-325."""
+        return engine.feature2density(self._binding, density_features)
+
+    def integrate_pos(self, pos_init, t, base_times):
+        """RK2 advection to ``base_times`` (models/tensorf_keyframe.py:575-611).  Returns the
+        advected positions; like the reference's eval branch it does not modify its inputs."""
+        out = engine.integrate_pos(self._binding, pos_init, t, base_times)
+        return out.reshape(pos_init.shape)
+
+    def compute_alpha(self, xyzt_locs, length=0.01, times=None, time_offset=None, transfer=False):
+        """models/tensorf_keyframe.py:508-537."""
+        shape = xyzt_locs.shape[:-1]
+        pts = self.normalize_coord(xyzt_locs[..., :3]).reshape(-1, 3)
+        t = xyzt_locs[..., -1:].reshape(-1, 1)
+        tsf = self.tmax / (self.num_keyframes - 1) if self.num_keyframes > 1 else 1
+        base = torch.zeros_like(t) if transfer else torch.round((t / tsf).clamp(0.0, self.num_keyframes - 1)) * tsf
+        prev = engine.integrate_pos(self._binding, pts, t, base)
+        xyzt = torch.cat([prev, self.normalize_time_coord(base)], dim=-1)
+        sigma = engine.density_sigma(self._binding, xyzt)
+        return (1 - torch.exp(-sigma * length)).view(shape)
+
+    # ---------------------------------------------------------------- regularisers (torch)
+    def density_L1(self):
+        total = 0
+        for k in range(3):
+            total = total + torch.mean(torch.abs(self.density_plane_space[k])) \
+                + torch.mean(torch.abs(1 - self.density_plane_time[k]))
+        return total
+
+    def TV_loss_density(self, reg):
+        total = 0
+        for k in range(3):
+            total = total + reg(self.density_plane_space[k]) * 1e-2 \
+                + ((reg(self.density_plane_time[k], t=True) * 1e-2) if self.num_keyframes > 1 else 0)
+        return total
+
+    def TV_loss_app(self, reg):
+        total = 0
+        for k in range(3):
+            total = total + reg(self.app_plane_space[k]) * 1e-2
+        return total
+
+    # ---------------------------------------------------------------- maintenance
+    @torch.no_grad()
+    def upsample_volume_grid(self, res_target, new_keyframes):
+        """Bilinear (align_corners) resize of every plane (models/tensorf_keyframe.py:326-376)."""
+        self.num_keyframes = new_keyframes
+        self.time_scale_factor = self.tmax / (new_keyframes - 1) if new_keyframes > 1 else 1
+        for space, time in ((self.app_plane_space, self.app_plane_time),
+                            (self.density_plane_space, self.density_plane_time)):
+            for i in range(3):
+                m0, m1 = MAT_MODE_SPACE[i]
+                n0, _ = MAT_MODE_TIME[i]
+                space[i] = nn.Parameter(F.interpolate(space[i].data, size=(res_target[m1], res_target[m0]),
+                                                      mode="bilinear", align_corners=True))
+                time[i] = nn.Parameter(F.interpolate(time[i].data, size=(new_keyframes, res_target[n0]),
+                                                     mode="bilinear", align_corners=True))
+        self.update_stepSize(res_target, verbose=False)
+
+    @torch.no_grad()
+    def getDenseAlpha(self, gridSize=None, transfer=False):
+        """Max over 60 time steps of alpha on a dense grid (models/tensorf_keyframe.py:461-499);
+        one advect + density kernel pair per time step instead of a per-slice loop."""
+        dev = self.aabb.device
+        samples = torch.stack(torch.meshgrid(torch.linspace(0, 1, gridSize[0]), torch.linspace(0, 1, gridSize[1]),
+                                             torch.linspace(0, 1, gridSize[2]), indexing="ij"), -1).to(dev)
+        dense_xyz = self.aabb[0] * (1 - samples) + self.aabb[1] * samples
+        alpha = torch.zeros_like(dense_xyz[..., 0])
+        flat = dense_xyz.view(-1, 3)
+        for t in np.linspace(0, 59, 60) / 60:
+            times = torch.ones_like(flat[..., -1:]) * t
+            cur = self.compute_alpha(torch.cat([flat, times], -1), self.stepSize, transfer=transfer)
+            alpha = torch.maximum(alpha, cur.view(alpha.shape))
+        return alpha, dense_xyz
+
+    @torch.no_grad()
+    def updateAlphaMask(self, gridSize=(200, 200, 200), transfer=False):
+        """models/tensorf_keyframe.py:378-405."""
+        gridSize = tuple(int(g) for g in gridSize)
+        alpha, dense_xyz = self.getDenseAlpha(gridSize, transfer=transfer)
+        dense_xyz = dense_xyz.transpose(0, 2).contiguous()
+        alpha = alpha.clamp(0, 1).transpose(0, 2).contiguous()[None, None]
+        alpha = F.max_pool3d(alpha, kernel_size=3, padding=1, stride=1).view(gridSize[::-1])
+        alpha[alpha >= self.alphaMask_thres] = 1
+        alpha[alpha < self.alphaMask_thres] = 0
+        self.alphaMask = AlphaGridMask(self.device, self.aabb, alpha)
+        valid_xyz = dense_xyz[alpha > 0.5]
+        return torch.stack((valid_xyz.amin(0), valid_xyz.amax(0)))
+
+    @torch.no_grad()
+    def shrink(self, new_aabb):
+        """Crop all planes to ``new_aabb`` (models/tensorf_keyframe.py:407-458)."""
+        lo, hi = new_aabb
+        t_l, b_r = (lo - self.aabb[0]) / self.units, (hi - self.aabb[0]) / self.units
+        t_l, b_r = torch.round(torch.round(t_l)).long(), torch.round(b_r).long() + 1
+        b_r = torch.stack([b_r, self.gridSize]).amin(0)
+        for i in range(3):
+            m0, m1 = MAT_MODE_SPACE[i]
+            n0, _ = MAT_MODE_TIME[i]
+            for space, time in ((self.density_plane_space, self.density_plane_time),
+                                (self.app_plane_space, self.app_plane_time)):
+                space[i] = nn.Parameter(space[i].data[..., t_l[m1]:b_r[m1], t_l[m0]:b_r[m0]].contiguous())
+                time[i] = nn.Parameter(time[i].data[..., :, t_l[n0]:b_r[n0]].contiguous())
+        if not torch.all(self.alphaMask.gridSize == self.gridSize):
+            t_l_r, b_r_r = t_l / (self.gridSize - 1), (b_r - 1) / (self.gridSize - 1)
+            correct = torch.zeros_like(new_aabb)
+            correct[0] = (1 - t_l_r) * self.aabb[0] + t_l_r * self.aabb[1]
+            correct[1] = (1 - b_r_r) * self.aabb[0] + b_r_r * self.aabb[1]
+            new_aabb = correct
+        newSize = b_r - t_l
+        self.aabb = new_aabb
+        self.update_stepSize((int(newSize[0]), int(newSize[1]), int(newSize[2])), verbose=False)
+
+    # ---------------------------------------------------------------- rendering
+    def render_rays(self, t, ray_o, ray_d, white_bg=True, transfer_vel=False, ray_chunk=None,
+                    jitter=None, chunk_bg=None, N_samples=-1):
+        """All chunks of one Renderer.forward call in one fused launch sequence.
+
+        In training mode the stratified jitter (one draw per ray) and, when the background
+        is not white, the per-chunk random-background draw come from the torch CPU generator
+        in the reference's order (models/tensorf_base.py:302-306,
+        models/tensorf_keyframe.py:740) unless passed in explicitly."""
+        ray_o = ray_o.reshape(-1, 3)
+        ray_d = ray_d.reshape(-1, 3)
+        n = ray_o.shape[0]
+        chunk = int(ray_chunk) if ray_chunk else max(n, 1)
+        n_chunks = n // chunk + int(n % chunk > 0)
+        training = self.training
+        if training and jitter is None:
+            jit, bgs = [], []
+            for c in range(n_chunks):
+                m = min(chunk, n - c * chunk)
+                jit.append(torch.rand(m, 1))
+                if not white_bg:
+                    bgs.append(bool(torch.rand((1,)) < 0.5))
+            jitter = torch.cat(jit, 0) if jit else torch.zeros(0, 1)
+            if not white_bg:
+                chunk_bg = torch.tensor(bgs, dtype=torch.uint8)
+        if not training:
+            jitter, chunk_bg = None, None
+        if N_samples is not None and N_samples > 0 and N_samples != self.nSamples:
+            saved = self.nSamples
+            self.nSamples = int(N_samples)
+            try:
+                return render_with_grad(self, t, ray_o, ray_d, white_bg, training, jitter, chunk_bg,
+                                        transfer_vel, chunk)
+            finally:
+                self.nSamples = saved
+        return render_with_grad(self, t, ray_o, ray_d, white_bg, training, jitter, chunk_bg,
+                                transfer_vel, chunk)
+
+    def forward(self, t, ray_o, ray_d, white_bg=True, ndc_ray=False, N_samples=-1, transfer_vel=False):
+        """One chunk (models/tensorf_keyframe.py:613-639): returns
+        (rgb_map, depth_map, acc_map, weights, mask_map)."""
+        if ndc_ray:
+            raise NotImplementedError("nvfi_b200: ndc rays are config-dead in the reference and unsupported")
+        return self.render_rays(t, ray_o, ray_d, white_bg=white_bg, transfer_vel=transfer_vel,
+                                ray_chunk=None, N_samples=N_samples)

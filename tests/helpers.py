@@ -102,3 +102,32 @@ def oracle_param_map(sc: O.Scene) -> Dict[str, torch.Tensor]:
             m[f"vel_net.{net}.{k}.weight"] = w
             m[f"vel_net.{net}.{k}.bias"] = b
     return m
+
+
+# ------------------------------------------------------------------------------------------
+# CUDA model construction from a golden fixture (used by the -m gpu tests)
+# ------------------------------------------------------------------------------------------
+def build_model(g: "Golden", device="cuda", alpha=False, mask_field=False, requires_grad=False):
+    """nvfi_b200.models.NVFi carrying the fixture's parameters."""
+    from nvfi_b200 import models as M
+    from nvfi_b200.synth import aabb_from_cfg
+
+    nv = M.NVFi(g.cfg, device, aabb_from_cfg(g.cfg), list(g.grid), [g.cfg.dataset.near, g.cfg.dataset.far])
+    nv = nv.to(device)
+    missing, unexpected = nv.load_state_dict({"nvfi." + k: v for k, v in g.sd.items()}, strict=False)
+    assert not unexpected, unexpected
+    bad = [m for m in missing if "frequency_bands" not in m and ".vel.vel_net." not in m and m != "nvfi.aabb"]
+    assert not bad, bad
+    f = nv.nvfi
+    if alpha:
+        vol = g.t("alpha/volume").float().to(device)
+        f.alphaMask = M.AlphaGridMask(device, f.aabb, vol)
+    if mask_field:
+        mf = M.MaskField(n_layer=4, n_dim=128, input_dim=3, skips=[], mask_dim=3, mask_act="softmax")
+        lins = list(mf.point_fc) + [mf.mask_fc]
+        for i, lin in enumerate(lins):
+            lin.weight.data.copy_(g.t(f"maskfield/{i}/weight"))
+            lin.bias.data.copy_(g.t(f"maskfield/{i}/bias"))
+        f.mask_field = mf.to(device)
+    nv.requires_grad_(requires_grad)
+    return nv
