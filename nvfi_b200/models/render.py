@@ -43,7 +43,7 @@ class Renderer(nn.Module):
         # the reference reshapes the 5th output to (..., 3) and therefore fails for
         # mask_dim != 3; reshape to its own width instead
         return (rgb.reshape(*shape, 3), depth.reshape(*shape), acc.reshape(*shape),
-                w.reshape(*shape, -1), extra.reshape(*shape, extra.shape[-1]))
+                w.reshape(*shape, w.shape[-1]), extra.reshape(*shape, extra.shape[-1]))
 
     def render(self, t, rays, white_background=False, mode="train", transfer_vel=False):
         if mode == "train":
