@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NVFI_ABI_VERSION 3
+#define NVFI_ABI_VERSION 4
 
 /* error codes */
 #define NVFI_OK 0
@@ -59,6 +59,8 @@ extern "C" {
 typedef struct NvfiLinear {
   const float* wt;
   const float* bias;
+  const float* w_rows; /* (128, k_pad) row-major = W zero padded, for the input-gradient GEMM
+                          of the backward pass; NULL when the layer is never differentiated */
   int32_t in_dim, out_dim; /* logical sizes */
   int32_t k_pad, n_pad;    /* padded sizes: k_pad % 32 == 0, n_pad % 4 == 0 */
 } NvfiLinear;
@@ -148,8 +150,10 @@ typedef struct NvfiRenderBuffers {
 } NvfiRenderBuffers;
 
 /* Upstream gradients and gradient accumulators for the backward pass.  Plane
- * gradients are accumulated in the packed (H, W, R) layout; nvfi_unpack_plane_grad
- * converts back to NCHW.  All accumulators must be zero-initialised by the caller. */
+ * gradients are accumulated (red.add) in the packed (H, W, R) layout — convert back with
+ * nvfi_unpack_plane; linear-layer gradients come out in the packed (k_pad, n_pad) layout
+ * of NvfiLinear.wt — convert back with nvfi_unpack_linear.  Every g_* accumulator must be
+ * zero-initialised by the caller; scratch buffers need no initialisation. */
 typedef struct NvfiRenderGrads {
   const float* g_rgb;     /* (n_rays, 3) or NULL */
   const float* g_depth;   /* (n_rays) or NULL */
@@ -159,21 +163,22 @@ typedef struct NvfiRenderGrads {
   float* g_dplane_time[3];
   float* g_aplane_space[3];
   float* g_aplane_time[3];
-  float* g_basis_mat;      /* packed (k_pad, n_pad) like NvfiLinear.wt */
+  float* g_basis_mat;      /* packed (k_pad, n_pad) */
   float* g_render_w[3];    /* packed */
-  float* g_render_b[3];
+  float* g_render_b[3];    /* (n_pad) */
   float* g_vel_w[NVFI_VEL_LAYERS]; /* packed */
   float* g_vel_b[NVFI_VEL_LAYERS];
   float* g_x_adv;          /* scratch (n_rays, S, 3) */
   float* g_sigma;          /* scratch (n_rays, S) */
-  float* partials;         /* scratch for per-CTA weight-gradient partial sums */
-  int64_t partials_bytes;
+  float* g_rgb_eff;        /* scratch (n_rays, 3): g_rgb after the clamp mask */
+  float* workspace;        /* scratch: per-CTA activation stash + weight-gradient partials */
+  int64_t workspace_bytes; /* >= nvfi_backward_workspace_bytes() */
 } NvfiRenderGrads;
 
 /* ---- library info --------------------------------------------------------------- */
 int nvfi_abi_version(void);
-/* Bytes of `partials` scratch nvfi_render_backward needs for this device. */
-int64_t nvfi_backward_partials_bytes(void);
+/* Bytes of `workspace` scratch nvfi_render_backward needs on the current device. */
+int64_t nvfi_backward_workspace_bytes(void);
 
 /* ---- layout packing ----------------------------------------------------------------
  * Replaces nothing in the reference (it reads NCHW through F.grid_sample,

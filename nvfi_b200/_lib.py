@@ -12,7 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnvfi_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 VEL_LAYERS = 6
 MAX_MASK_LAYERS = 8
 
@@ -27,7 +27,7 @@ P3 = C.c_void_p * 3
 
 
 class NvfiLinear(C.Structure):
-    _fields_ = [("wt", C.c_void_p), ("bias", C.c_void_p), ("in_dim", C.c_int32),
+    _fields_ = [("wt", C.c_void_p), ("bias", C.c_void_p), ("w_rows", C.c_void_p), ("in_dim", C.c_int32),
                 ("out_dim", C.c_int32), ("k_pad", C.c_int32), ("n_pad", C.c_int32)]
 
 
@@ -77,8 +77,8 @@ class NvfiRenderGrads(C.Structure):
         ("g_aplane_time", P3), ("g_basis_mat", C.c_void_p),
         ("g_render_w", P3), ("g_render_b", P3),
         ("g_vel_w", C.c_void_p * VEL_LAYERS), ("g_vel_b", C.c_void_p * VEL_LAYERS),
-        ("g_x_adv", C.c_void_p), ("g_sigma", C.c_void_p), ("partials", C.c_void_p),
-        ("partials_bytes", C.c_int64),
+        ("g_x_adv", C.c_void_p), ("g_sigma", C.c_void_p), ("g_rgb_eff", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -88,7 +88,7 @@ _lib: Optional[C.CDLL] = None
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES = {
     "nvfi_abi_version": (_i, []),
-    "nvfi_backward_partials_bytes": (_i64, []),
+    "nvfi_backward_workspace_bytes": (_i64, []),
     "nvfi_pack_plane": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "nvfi_unpack_plane": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "nvfi_pack_linear": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -306,9 +306,9 @@ __device__ __forceinline__ void cp_async_wait() {
 // for n < 128 (in place).  256 threads; thread (tm, tn) owns rows {4tm..4tm+3, 64+4tm..+3}
 // x columns {8tn..8tn+7}.  W^T streams through a 2-stage cp.async ring of 32 k-rows
 // (16 KB) per stage.  Rows of actT in [in_dim, k_pad) must be zero (finite).
-template <int ACT>
+template <int ACT, int RS = NVFI_TM, bool STASH = false>
 __device__ void tile_linear128(float* __restrict__ actT, float* __restrict__ wS,
-                               const NvfiLinear& L) {
+                               const NvfiLinear& L, float* __restrict__ stash = nullptr) {
   const int tid = threadIdx.x;
   const int tm = tid & 15, tn = tid >> 4;
   float acc[8][8];
@@ -336,11 +336,11 @@ __device__ void tile_linear128(float* __restrict__ actT, float* __restrict__ wS,
     }
     __syncthreads();
     const float* w = wS + (c & 1) * (NVFI_KC * 128) + tn * 8;
-    const float* a = actT + c * (NVFI_KC * NVFI_TM) + tm * 4;
+    const float* a = actT + c * (NVFI_KC * RS) + tm * 4;
 #pragma unroll 4
     for (int kk = 0; kk < NVFI_KC; ++kk) {
-      const float4 a0 = *reinterpret_cast<const float4*>(a + kk * NVFI_TM);
-      const float4 a1 = *reinterpret_cast<const float4*>(a + kk * NVFI_TM + 64);
+      const float4 a0 = *reinterpret_cast<const float4*>(a + kk * RS);
+      const float4 a1 = *reinterpret_cast<const float4*>(a + kk * RS + 64);
       const float4 w0 = *reinterpret_cast<const float4*>(w + kk * 128);
       const float4 w1 = *reinterpret_cast<const float4*>(w + kk * 128 + 4);
       const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
@@ -357,17 +357,23 @@ __device__ void tile_linear128(float* __restrict__ actT, float* __restrict__ wS,
   for (int j = 0; j < 8; ++j) {
     const int n = tn * 8 + j;
     const float bv = L.bias ? __ldg(L.bias + n) : 0.f;
+    float4 h0 = make_float4(acc[0][j] + bv, acc[1][j] + bv, acc[2][j] + bv, acc[3][j] + bv);
+    float4 h1 = make_float4(acc[4][j] + bv, acc[5][j] + bv, acc[6][j] + bv, acc[7][j] + bv);
+    if (STASH) {  // pre-activations, (128, 128) row-major per layer, for the backward pass
+      *reinterpret_cast<float4*>(stash + n * NVFI_TM + tm * 4) = h0;
+      *reinterpret_cast<float4*>(stash + n * NVFI_TM + 64 + tm * 4) = h1;
+    }
     float4 o0, o1;
-    o0.x = activate<ACT>(acc[0][j] + bv);
-    o0.y = activate<ACT>(acc[1][j] + bv);
-    o0.z = activate<ACT>(acc[2][j] + bv);
-    o0.w = activate<ACT>(acc[3][j] + bv);
-    o1.x = activate<ACT>(acc[4][j] + bv);
-    o1.y = activate<ACT>(acc[5][j] + bv);
-    o1.z = activate<ACT>(acc[6][j] + bv);
-    o1.w = activate<ACT>(acc[7][j] + bv);
-    *reinterpret_cast<float4*>(actT + n * NVFI_TM + tm * 4) = o0;
-    *reinterpret_cast<float4*>(actT + n * NVFI_TM + 64 + tm * 4) = o1;
+    o0.x = activate<ACT>(h0.x);
+    o0.y = activate<ACT>(h0.y);
+    o0.z = activate<ACT>(h0.z);
+    o0.w = activate<ACT>(h0.w);
+    o1.x = activate<ACT>(h1.x);
+    o1.y = activate<ACT>(h1.y);
+    o1.z = activate<ACT>(h1.z);
+    o1.w = activate<ACT>(h1.w);
+    *reinterpret_cast<float4*>(actT + n * RS + tm * 4) = o0;
+    *reinterpret_cast<float4*>(actT + n * RS + 64 + tm * 4) = o1;
   }
   __syncthreads();
 }
@@ -375,7 +381,7 @@ __device__ void tile_linear128(float* __restrict__ actT, float* __restrict__ wS,
 // Narrow output layer (n_pad <= 2*NH): thread handles sample m = tid & 127 and output
 // columns [half*nh, half*nh + nh) with half = tid >> 7, nh = n_pad / 2.  Results go to
 // outS[n][m] (a separate shared buffer, n < n_pad), then a barrier.
-template <int NH>
+template <int NH, int RS = NVFI_TM>
 __device__ void tile_linear_small(const float* __restrict__ actT, float* __restrict__ outS,
                                   const NvfiLinear& L) {
   const int tid = threadIdx.x;
@@ -387,7 +393,7 @@ __device__ void tile_linear_small(const float* __restrict__ actT, float* __restr
   for (int j = 0; j < NH; ++j) acc[j] = 0.f;
   const float* wt = L.wt + n0;
   for (int k = 0; k < L.in_dim; ++k) {
-    const float a = actT[k * NVFI_TM + m];
+    const float a = actT[k * RS + m];
     const float* wr = wt + (size_t)k * L.n_pad;
 #pragma unroll
     for (int j = 0; j < NH; ++j)
@@ -401,6 +407,7 @@ __device__ void tile_linear_small(const float* __restrict__ actT, float* __restr
 
 // PositionEncoder(3) of (x, y, z, t) into rows 0..31 of actT (28 values + 4 zero rows)
 // (models/base_network.py:42-54).  256 threads: two threads per sample.
+template <int RS = NVFI_TM>
 __device__ __forceinline__ void vel_encode_tile(float* __restrict__ actT, const float* xs,
                                                 const float* ys, const float* zs, const float* ts) {
   const int tid = threadIdx.x;
@@ -409,35 +416,39 @@ __device__ __forceinline__ void vel_encode_tile(float* __restrict__ actT, const 
   if (part == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      actT[i * NVFI_TM + m] = q[i];
+      actT[i * RS + m] = q[i];
       float s, c;
       sincosf(q[i], &s, &c);
-      actT[(4 + i) * NVFI_TM + m] = s;
-      actT[(8 + i) * NVFI_TM + m] = c;
-      actT[(12 + i) * NVFI_TM + m] = sinf(q[i] * 2.f);
+      actT[(4 + i) * RS + m] = s;
+      actT[(8 + i) * RS + m] = c;
+      actT[(12 + i) * RS + m] = sinf(q[i] * 2.f);
     }
   } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      actT[(16 + i) * NVFI_TM + m] = cosf(q[i] * 2.f);
+      actT[(16 + i) * RS + m] = cosf(q[i] * 2.f);
       float s, c;
       sincosf(q[i] * 4.f, &s, &c);
-      actT[(20 + i) * NVFI_TM + m] = s;
-      actT[(24 + i) * NVFI_TM + m] = c;
-      actT[(28 + i) * NVFI_TM + m] = 0.f;
+      actT[(20 + i) * RS + m] = s;
+      actT[(24 + i) * RS + m] = c;
+      actT[(28 + i) * RS + m] = 0.f;
     }
   }
   __syncthreads();
 }
 
 // Weight net of VelBasis on a tile: inputs (x,y,z,t)[m] -> outS[0..5][m] (6 basis weights).
-template <int ACT>
+// With STASH the pre-activations of the 5 hidden layers go to stash[l] (128x128 each).
+template <int ACT, int RS = NVFI_TM, bool STASH = false>
 __device__ void vel_net_tile(const NvfiLinear* net, float* actT, float* wS, float* outS,
-                             const float* xs, const float* ys, const float* zs, const float* ts) {
-  vel_encode_tile(actT, xs, ys, zs, ts);
+                             const float* xs, const float* ys, const float* zs, const float* ts,
+                             float* stash = nullptr) {
+  vel_encode_tile<RS>(actT, xs, ys, zs, ts);
 #pragma unroll 1
-  for (int l = 0; l < NVFI_VEL_LAYERS - 1; ++l) tile_linear128<ACT>(actT, wS, net[l]);
-  tile_linear_small<4>(actT, outS, net[NVFI_VEL_LAYERS - 1]);
+  for (int l = 0; l < NVFI_VEL_LAYERS - 1; ++l)
+    tile_linear128<ACT, RS, STASH>(actT, wS, net[l],
+                                   STASH ? stash + (size_t)l * NVFI_TM * NVFI_TM : nullptr);
+  tile_linear_small<4, RS>(actT, outS, net[NVFI_VEL_LAYERS - 1]);
 }
 
 // Shared memory of one RK2 advection tile.

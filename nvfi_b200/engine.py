@@ -61,7 +61,8 @@ class _Tracked:
 class PackedLinear:
     """nn.Linear weight (out,in)[, bias] -> zero-padded W^T (k_pad, n_pad) [+ (n_pad)]."""
 
-    def __init__(self, out_dim: int, in_dim: int, device, hidden: bool, has_bias: bool = True):
+    def __init__(self, out_dim: int, in_dim: int, device, hidden: bool, has_bias: bool = True,
+                 diff: bool = False):
         self.out_dim, self.in_dim = out_dim, in_dim
         self.k_pad = _round_up(in_dim, 32)
         self.n_pad = 128 if hidden else _round_up(out_dim, 4)
@@ -69,6 +70,9 @@ class PackedLinear:
             raise RuntimeError(f"nvfi_b200: hidden width {out_dim} unsupported (kernels are built for 128)")
         self.wt = torch.zeros(self.k_pad, self.n_pad, device=device, dtype=torch.float32)
         self.bias = torch.zeros(self.n_pad, device=device, dtype=torch.float32) if has_bias else None
+        # W zero-padded to (128, k_pad) for the input-gradient GEMM of the backward pass
+        self.w_rows = (torch.zeros(128, self.k_pad, device=device, dtype=torch.float32)
+                       if (hidden and diff) else None)
         self.track = _Tracked()
 
     def sync(self, w: torch.Tensor, b: Optional[torch.Tensor]):
@@ -80,10 +84,13 @@ class PackedLinear:
         L.check(lib.nvfi_pack_linear(wd.data_ptr(), _ptr(bd), self.wt.data_ptr(), _ptr(self.bias),
                                      self.out_dim, self.in_dim, self.k_pad, self.n_pad, _stream()),
                 "pack_linear")
+        if self.w_rows is not None:
+            self.w_rows[:self.out_dim, :self.in_dim].copy_(wd)
 
     def fill(self, s: L.NvfiLinear):
         s.wt = self.wt.data_ptr()
         s.bias = _ptr(self.bias)
+        s.w_rows = _ptr(self.w_rows)
         s.in_dim, s.out_dim, s.k_pad, s.n_pad = self.in_dim, self.out_dim, self.k_pad, self.n_pad
 
     def unpack_grad(self, g_wt: torch.Tensor, g_b: Optional[torch.Tensor], want_bias: bool):
@@ -210,7 +217,7 @@ class FieldBinding:
             mlp = f.renderModule.mlp
             lins = [mlp[0], mlp[2], mlp[4]]
             if self.render is None or self.render[0].in_dim != lins[0].in_features:
-                self.render = [PackedLinear(l.out_features, l.in_features, dev, hidden=(i < 2))
+                self.render = [PackedLinear(l.out_features, l.in_features, dev, hidden=(i < 2), diff=True)
                                for i, l in enumerate(lins)]
             for i, l in enumerate(lins):
                 self.render[i].sync(l.weight, l.bias)
@@ -220,7 +227,7 @@ class FieldBinding:
         if f.use_vel:
             if self.vel is None:
                 dims = [(128, 28)] + [(128, 128)] * 4 + [(6, 128)]
-                self.vel = [PackedLinear(o, i, dev, hidden=(j < 5)) for j, (o, i) in enumerate(dims)]
+                self.vel = [PackedLinear(o, i, dev, hidden=(j < 5), diff=True) for j, (o, i) in enumerate(dims)]
                 self.acc = [PackedLinear(o, i, dev, hidden=(j < 5)) for j, (o, i) in enumerate(dims)]
             for j, (w, b) in enumerate(vel_linears(f.vel_net.weight_net)):
                 self.vel[j].sync(w, b)
@@ -366,6 +373,87 @@ def render_forward(binding: FieldBinding, rays_o: torch.Tensor, rays_d: torch.Te
     o.args = (a, b)
     o.keep = (rays_o, rays_d, jitter, chunk_bg)
     return o
+
+
+DEBUG_KEEP: Optional[dict] = None   # tests may set this to a dict to receive backward intermediates
+
+
+def render_backward(binding: FieldBinding, out: RenderOutputs, g_rgb, g_depth, g_acc, g_w,
+                    needs: Sequence[bool]):
+    """nvfi_render_backward + conversion of the packed gradients to the parameter layouts.
+    Returns gradients in the order of ``autograd._diff_params``."""
+    lib = L.load()
+    s = binding.s          # parameters are unchanged since forward (checked by the caller)
+    a, b = out.args
+    dev = out.weights.device
+    n, S = out.weights.shape
+    f32 = dict(device=dev, dtype=torch.float32)
+
+    def cg(g, shape):
+        if g is None:
+            return None
+        g = g.detach().to(**f32).expand(shape).contiguous()
+        return g
+
+    g_rgb, g_depth = cg(g_rgb, (n, 3)), cg(g_depth, (n,))
+    g_acc, g_w = cg(g_acc, (n,)), cg(g_w, (n, S))
+    d = L.NvfiRenderGrads()
+    d.g_rgb, d.g_depth, d.g_acc, d.g_weights = _ptr(g_rgb), _ptr(g_depth), _ptr(g_acc), _ptr(g_w)
+    keep = []
+    gp = {}
+    for name, dst in (("density_plane_space", d.g_dplane_space), ("density_plane_time", d.g_dplane_time),
+                      ("app_plane_space", d.g_aplane_space), ("app_plane_time", d.g_aplane_time)):
+        gp[name] = []
+        for k in range(3):
+            R, H, W = binding.planes[name][k].shape
+            g = torch.zeros(H, W, R, **f32)
+            gp[name].append(g)
+            dst[k] = g.data_ptr()
+    g_basis = torch.zeros_like(binding.basis.wt)
+    d.g_basis_mat = g_basis.data_ptr()
+    g_rw, g_rb = [], []
+    mlp_mode = s.shading_mode == L.SHADING_MLP_PE
+    if mlp_mode:
+        for i in range(3):
+            g_rw.append(torch.zeros_like(binding.render[i].wt))
+            g_rb.append(torch.zeros_like(binding.render[i].bias))
+            d.g_render_w[i], d.g_render_b[i] = g_rw[i].data_ptr(), g_rb[i].data_ptr()
+    g_vw, g_vb = [], []
+    if s.use_vel:
+        for j in range(L.VEL_LAYERS):
+            g_vw.append(torch.zeros_like(binding.vel[j].wt))
+            g_vb.append(torch.zeros_like(binding.vel[j].bias))
+            d.g_vel_w[j], d.g_vel_b[j] = g_vw[j].data_ptr(), g_vb[j].data_ptr()
+    g_x = torch.empty(n, S, 3, **f32)
+    g_sig = torch.empty(n, S, **f32)
+    g_eff = torch.empty(n, 3, **f32)
+    ws_bytes = int(lib.nvfi_backward_workspace_bytes())
+    ws = torch.empty(ws_bytes // 4, **f32)
+    d.g_x_adv, d.g_sigma, d.g_rgb_eff = g_x.data_ptr(), g_sig.data_ptr(), g_eff.data_ptr()
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws_bytes
+    L.check(lib.nvfi_render_backward(C.byref(s), C.byref(a), C.byref(b), C.byref(d), _stream()),
+            "render_backward")
+    if DEBUG_KEEP is not None:
+        DEBUG_KEEP.update(g_sigma=g_sig, g_x_adv=g_x, g_rgb_eff=g_eff, fwd=out)
+    grads: List[Optional[torch.Tensor]] = []
+    for name in ("density_plane_space", "density_plane_time", "app_plane_space", "app_plane_time"):
+        for k in range(3):
+            grads.append(binding.planes[name][k].unpack_grad(gp[name][k]))
+    grads.append(binding.basis.unpack_grad(g_basis, None, False)[0])
+    if mlp_mode:
+        for i in range(3):
+            gw, gb = binding.render[i].unpack_grad(g_rw[i], g_rb[i], True)
+            grads += [gw, gb]
+    if s.use_vel:
+        advected = bool(a.advect)
+        for j in range(L.VEL_LAYERS):
+            if advected:
+                gw, gb = binding.vel[j].unpack_grad(g_vw[j], g_vb[j], True)
+            else:   # keyframe render: the velocity net is not on the graph (reference: grad None)
+                gw, gb = None, None
+            grads += [gw, gb]
+    assert len(grads) == len(needs), (len(grads), len(needs))
+    return [g if need else None for g, need in zip(grads, needs)]
 
 
 # ------------------------------------------------------------------------------------------
