@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py — rays/s of the NVFi train step (render forward + MSE + hand-written backward)
+on the BASELINE.json workload: bat.yaml, one 800x800 frame (640 000 rays) per GPU per step,
+192 samples/ray, final 199^3 grid, K = 16 keyframes, non-keyframe time (every valid sample is
+advected by one RK2 step = 2 velocity-MLP evaluations).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  Keys (see DESIGN.md "Measurement"):
+  value         whole-job rays/s, inputs resident in HBM, CUDA events, max over ranks
+  e2e           same metric through the public API (models.Renderer.render + loss.backward +
+                loss.item()) with HOST ray / target buffers: H2D and D2H inside the timed region
+  roofline      dominant kernel: algorithmic FLOPs (or bytes) per launch / its CUDA-event time,
+                measured live through the library's per-launch event hook (no profiler)
+  kernels       the same for every kernel of the step
+  cpu_baseline  the CPU oracle (a torch restatement of the reference algorithm) on a bounded
+                sample of the same workload, all host threads
+  --impl reference  times only that CPU leg (the reference has no native code and cannot travel
+                to the GPU box; the oracle port is pinned to it by tests/golden/*)
+Multi-GPU: weak scaling — every rank renders its own 800x800 frame (a different camera of the
+same scene) and the ranks exchange ONE all-reduce of the flat gradient buffer per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "rays/sec (train step, 800x800, 192 samples/ray)"
+UNIT = "rays/s"
+H = W = 800
+GRID = (199, 199, 199)
+STEP_RATIO = 1.79          # update_stepSize then computes nSamples = 192 spanning the box
+T_RENDER = 0.33            # non-keyframe time: base 0.35, one RK2 step backwards
+RAY_CHUNK = 2048           # the reference's chunk size (renderer.n_rays)
+VEL_EVAL_FLOP = 2 * (28 * 128 + 4 * 128 * 128 + 128 * 6)     # 139 776
+APP_EVAL_FLOP = 2 * (110 * 128 + 128 * 128 + 128 * 3) + 2 * 48 * 32   # 61 696 + 3 072
+DENSITY_BYTES = 6 * 4 * 24 * 4    # 2 304 B per valid sample
+APP_BYTES = 6 * 4 * 48 * 4        # 4 608 B per appearance sample
+
+
+def env_world():
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+            int(os.environ.get("WORLD_SIZE", 1)))
+
+
+def workload_config(world):
+    return {"workload": "bat.yaml 800x800 frame per GPU, 192 samples/ray (step_ratio 1.79 @199^3), "
+                        "K=16, t=0.33 (1 RK2 step), train step = render fwd + MSE + bwd",
+            "rays_per_step_per_gpu": H * W, "samples_per_ray": 192, "grid": list(GRID),
+            "ray_chunk": RAY_CHUNK, "parallelism": f"ray-sharded dp{world}",
+            "l2": "per-sample buffers (6 GB/step) exceed L2; the 37 MB factor planes are L2-resident by design"}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU leg (oracle port of the reference algorithm)
+# ------------------------------------------------------------------------------------------
+class CpuLeg:
+    """Reference algorithm (oracle port) on the host: train render fwd + MSE + backward on
+    2048-ray chunks of the same frame, all host threads."""
+
+    def __init__(self):
+        from nvfi_b200 import configs, synth
+        from nvfi_b200.scenes import frame_rays
+        from oracle.scene_io import scene_from_state
+
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        cfg = configs.get_config("bat", step_ratio=STEP_RATIO)
+        K = int(cfg.nvfi.num_keyframes)
+        sd = synth.synth_state(cfg, list(GRID), K, seed=233)
+        self.sc = scene_from_state(cfg, list(GRID), K, sd, requires_grad=True)
+        self.o, self.d = frame_rays(H, W)
+        self.gen = torch.Generator().manual_seed(7)
+        self.next_chunk = 0
+
+    def run(self, budget_s: float, chunks_cap: int):
+        """Returns (seconds, rays) for up to `chunks_cap` chunks or `budget_s` seconds."""
+        from oracle import nvfi_oracle as O
+        start = (H // 2) * W    # chunks from the middle of the frame (rays that hit the cube)
+        done, t_total, k = 0, 0.0, 0
+        while k < chunks_cap and (k < 1 or t_total < budget_s):
+            c = self.next_chunk % 64
+            sl = slice(start + c * RAY_CHUNK, start + (c + 1) * RAY_CHUNK)
+            oo, dd = self.o[sl], self.d[sl]
+            jit = torch.rand(oo.shape[0], 1, generator=self.gen)
+            target = torch.rand(oo.shape[0], 3, generator=self.gen)
+            for p in self.sc.parameters():
+                p.grad = None
+            t0 = time.perf_counter()
+            out = O.render_chunk(self.sc, T_RENDER, oo, dd, white_bg=True, training=True, jitter=jit)
+            loss = torch.nn.functional.mse_loss(out[0], target)
+            loss.backward()
+            t_total += time.perf_counter() - t0
+            done += oo.shape[0]
+            k += 1
+            self.next_chunk += 1
+        return t_total, done, k
+
+
+def cpu_sample_desc(k):
+    return f"{k} chunks x {RAY_CHUNK} rays from the frame centre, fwd+MSE+bwd, t={T_RENDER}"
+
+
+def run_reference(args):
+    rank, _, world = env_world()
+    if rank != 0:
+        return
+    steps, warm = max(1, min(args.steps, 8)), min(max(0, args.warmup), 1)
+    leg = CpuLeg()
+    for _ in range(warm):
+        leg.run(0.0, 1)
+    t_sum, r_sum = 0.0, 0
+    for _ in range(steps):      # each step = a bounded sample of the frame: 2 chunks
+        tt, rr, _ = leg.run(1e9, 2)
+        t_sum += tt
+        r_sum += rr
+    value = r_sum / t_sum
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": 1e3 * t_sum / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(world),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": leg.cores, "kind": "port",
+                             "sample": cpu_sample_desc(2) + " per step"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.path = tempfile.mktemp(prefix="nvfi_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            ident = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+        except Exception:
+            ident = str(device_index)
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ident, f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        rows = []
+        try:
+            for ln in open(self.path):
+                p = [x.strip() for x in ln.split(",")]
+                if len(p) >= 7:
+                    rows.append(p)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if not rows:
+            return out
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
+        out.update(sm_mhz=sm[len(sm) // 2] if sm else None,
+                   sm_max_mhz=float(rows[0][1]) if rows[0][1].replace(".", "").isdigit() else None,
+                   power_w_max=max((float(r[2]) for r in rows if r[2].replace(".", "").isdigit()), default=None),
+                   reasons=reasons, samples=len(rows))
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"hbm_gbs": float(j["hbm_gbs"]), "bf16_tflops": float(j["bf16_tflops"]),
+                "bf16_tflops_sustained": float(j.get("bf16_tflops_sustained", j["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    from nvfi_b200 import _lib, engine, sharding
+    from nvfi_b200 import models as M
+    from nvfi_b200.scenes import build_scene, frame_rays
+
+    rank, local_rank, world = env_world()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the nvfi_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()     # fail loudly when the CUDA library is missing
+
+    cfg, nv, _ = build_scene("bat", grid=GRID, device=dev, step_ratio=STEP_RATIO)
+    field = nv.nvfi
+    assert field.nSamples == 192, field.nSamples
+    nv.requires_grad_(True)
+    renderer = M.Renderer(nv, 0, 0, RAY_CHUNK)
+    n = H * W
+    # weak scaling: every rank renders its own camera of the same scene
+    o_h, d_h = frame_rays(H, W, theta=30.0 + 9.0 * rank)
+    gen = torch.Generator().manual_seed(1000 + rank)
+    target_h = torch.rand(n, 3, generator=gen)
+    jitter_h = torch.rand(n, 1, generator=gen)
+    o_h, d_h, target_h, jitter_h = (x.pin_memory() for x in (o_h, d_h, target_h, jitter_h))
+    o_d, d_d, target_d, jitter_d = (x.to(dev) for x in (o_h, d_h, target_h, jitter_h))
+    params = [p for p in nv.parameters()]
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    def step_resident():
+        """Hot path with inputs resident in HBM."""
+        for p in params:
+            p.grad = None
+        field.train()
+        rgb, depth, acc, w, _ = field.render_rays(T_RENDER, o_d, d_d, white_bg=True, ray_chunk=RAY_CHUNK,
+                                                  jitter=jitter_d)
+        loss = torch.nn.functional.mse_loss(rgb, target_d)
+        loss.backward()
+        if world > 1:
+            sharding.allreduce_grads(params, average=True)
+        return loss
+
+    def step_e2e():
+        """Public API, host buffers: Ray.to(device) + Renderer.render(mode='train') + MSE + backward
+        + loss.item() (what one iteration of train_nvfi.py does around the render, :156-164, :241-252)."""
+        for p in params:
+            p.grad = None
+        rays = M.Ray(o_h, d_h, cfg.dataset.near, cfg.dataset.far).to(dev, non_blocking=True)
+        tgt = target_h.to(dev, non_blocking=True)
+        rgb, depth, acc, w, _ = renderer.render(T_RENDER, rays, white_background=True, mode="train")
+        loss = torch.nn.functional.mse_loss(rgb, tgt)
+        loss.backward()
+        if world > 1:
+            sharding.allreduce_grads(params, average=True)
+        return float(loss.item()), rays
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    K, Wm = max(1, args.steps), max(3, args.warmup)
+    for _ in range(Wm):
+        step_resident()
+    launches0 = _lib.launch_count()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    ms_total = timed(step_resident, K)
+    clk = clocks.stop() if clocks else None
+    launches = (_lib.launch_count() - launches0)
+    ms_step = ms_total / K
+    value = world * n / (ms_step * 1e-3)
+
+    # ---- e2e through the public API with host buffers
+    step_e2e()
+    ms_e2e = timed(step_e2e, K) / K
+    _, rays_obj = step_e2e()
+    h2d = sum(b.numel() * b.element_size() for b in rays_obj.buffers()) + target_h.numel() * 4 + n * 4
+    e2e = {"value": world * n / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+           "api": "models.Ray.to(device) + models.Renderer.render(mode='train') + mse + backward + loss.item()"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world), "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clk}
+
+    # ---- per-kernel device time (CUDA events around every launch, on the launching stream)
+    if rank == 0:
+        out = engine.render_forward(field.binding, o_d, d_d, T_RENDER, white_bg=True, training=True,
+                                    jitter=jitter_d, ray_chunk=RAY_CHUNK, want_stats=True)
+        torch.cuda.synchronize()
+        n_valid, n_adv, n_app, _ = (int(x) for x in out.stats.tolist())
+        del out
+        _lib.profile_read(reset=True)
+        _lib.profile_enable(True)
+        P = 2
+        for _ in range(P):
+            step_resident()
+        prof = _lib.profile_read(reset=True)
+        _lib.profile_enable(False)
+        cnt = engine.LAST_BWD_COUNTERS.view(torch.int64).tolist()
+        n_app_bwd, n_adv_bwd = int(cnt[4]), int(cnt[5])
+        pk = peaks()
+        tf32_peak = 0.5 * pk["bf16_tflops_sustained"]
+        S = 192
+        alg = {   # kernel -> (bound, algorithmic work per launch)
+            "k_sample_advect": ("tensor", n_adv * 2 * VEL_EVAL_FLOP),
+            "k_advect_bwd": ("tensor", n_adv_bwd * 6 * VEL_EVAL_FLOP),   # 2 evals: fwd recompute + dX + dW GEMMs
+            "k_march": ("hbm", n_valid * DENSITY_BYTES + n * (44 + 4 * S)),
+            "k_density_bwd": ("hbm", n_valid * 2 * DENSITY_BYTES),
+            "k_appearance": ("hbm", n_app * APP_BYTES),
+            "k_app_bwd": ("hbm", n_app_bwd * 3 * APP_BYTES),
+            "k_march_bwd": ("hbm", n * S * (4 + 4 + 1 + 4) + n * 40),
+            "k_composite": ("hbm", n * S * 4 + n_app * 12 + n * 12),
+        }
+        total_ms = sum(v[0] for v in prof.values())
+        kern = {}
+        for name, (ms, cnt_l) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+            e = {"ms_per_launch": ms / cnt_l, "launches_per_step": cnt_l / P, "share": ms / total_ms}
+            if name in alg:
+                bound, work = alg[name]
+                sec = (ms / cnt_l) * 1e-3
+                if bound == "tensor":
+                    ach = work / sec / 1e12
+                    e.update(bound="tensor", achieved=ach, peak=tf32_peak, unit="TFLOP/s", frac=ach / tf32_peak)
+                else:
+                    ach = work / sec / 1e9
+                    e.update(bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"])
+            kern[name] = e
+        top = next(iter(kern))
+        r = dict(kern[top])
+        line["roofline"] = {"kernel": top, "bound": r.get("bound"), "achieved": r.get("achieved"),
+                            "peak": r.get("peak"), "unit": r.get("unit"), "frac": r.get("frac"),
+                            "traffic": None, "share_of_step": r["share"],
+                            "peak_source": pk["source"] + ("; TF32 peak = 0.5 x measured sustained bf16"
+                                                            if r.get("bound") == "tensor" else "")}
+        line["roofline_gather"] = dict(kern.get("k_march", {}), kernel="k_march",
+                                       note="TensoRF density gather + alpha scan; planes are L2-resident, "
+                                            "so algorithmic GB/s may exceed the HBM copy peak")
+        line["kernels"] = kern
+        line["counts"] = {"valid_samples": n_valid, "advected_samples": n_adv, "app_samples": n_app,
+                          "app_samples_bwd": n_app_bwd, "advected_samples_bwd": n_adv_bwd}
+        if world == 1 and not args.no_cpu:
+            leg = CpuLeg()
+            leg.run(0.0, 1)     # warm-up chunk (thread pool, allocator)
+            tt, rr, k = leg.run(args.cpu_budget, 8)
+            line["cpu_baseline"] = {"value": rr / tt, "unit": UNIT, "cores": leg.cores, "kind": "port",
+                                    "sample": cpu_sample_desc(k)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(device_ids=[local_rank])
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="nvfi_b200", choices=["nvfi_b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

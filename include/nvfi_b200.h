@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NVFI_ABI_VERSION 4
+#define NVFI_ABI_VERSION 5
 
 /* error codes */
 #define NVFI_OK 0
@@ -145,7 +145,9 @@ typedef struct NvfiRenderBuffers {
   float* sigma;     /* (n_rays, S) density (saved for backward), may be NULL in eval */
   /* small */
   uint8_t* chunk_inside; /* (n_chunks) */
-  int32_t* counters;     /* >= 16 ints, zeroed by the callee */
+  int32_t* counters;     /* >= 16 ints (8-byte aligned), zeroed by the callee.  After
+                            nvfi_render_backward, the int64 at [8] / [10] holds the number of
+                            samples back-propagated through the appearance / velocity nets */
   int64_t* stats;        /* >= 4: [valid samples, advected samples, app samples, 0], or NULL */
 } NvfiRenderBuffers;
 
@@ -179,6 +181,21 @@ typedef struct NvfiRenderGrads {
 int nvfi_abi_version(void);
 /* Bytes of `workspace` scratch nvfi_render_backward needs on the current device. */
 int64_t nvfi_backward_workspace_bytes(void);
+
+/* ---- instrumentation ---------------------------------------------------------------
+ * Not part of the reference surface.  nvfi_launch_count: kernels this library has launched
+ * since it was loaded (bench.py's `gpu_launches`).  With profiling enabled every launch is
+ * bracketed by two CUDA events on its stream; nvfi_profile_read synchronises the device and
+ * returns per-kernel totals (bench.py's live `roofline` timing — no profiler attached). */
+typedef struct NvfiProfileEntry {
+  char name[48];
+  double ms;        /* summed device time of the launches */
+  int64_t launches;
+} NvfiProfileEntry;
+int64_t nvfi_launch_count(void);
+int nvfi_profile_enable(int on);
+/* Fills up to `cap` entries; returns the number filled (< 0 on error).  reset != 0 clears. */
+int nvfi_profile_read(NvfiProfileEntry* out, int cap, int reset);
 
 /* ---- layout packing ----------------------------------------------------------------
  * Replaces nothing in the reference (it reads NCHW through F.grid_sample,

@@ -12,7 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnvfi_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 VEL_LAYERS = 6
 MAX_MASK_LAYERS = 8
 
@@ -82,6 +82,10 @@ class NvfiRenderGrads(C.Structure):
     ]
 
 
+class NvfiProfileEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("ms", C.c_double), ("launches", C.c_int64)]
+
+
 _lib: Optional[C.CDLL] = None
 
 # name -> (restype, argtypes); every symbol include/nvfi_b200.h declares
@@ -89,6 +93,9 @@ _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES = {
     "nvfi_abi_version": (_i, []),
     "nvfi_backward_workspace_bytes": (_i64, []),
+    "nvfi_launch_count": (_i64, []),
+    "nvfi_profile_enable": (_i, [_i]),
+    "nvfi_profile_read": (_i, [C.POINTER(NvfiProfileEntry), _i, _i]),
     "nvfi_pack_plane": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "nvfi_unpack_plane": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "nvfi_pack_linear": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -131,6 +138,23 @@ def load(path: Optional[str] = None) -> C.CDLL:
     if path is None:
         _lib = lib
     return lib
+
+
+def launch_count() -> int:
+    return int(load().nvfi_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    check(load().nvfi_profile_enable(1 if on else 0), "profile_enable")
+
+
+def profile_read(reset: bool = True) -> dict:
+    """{kernel name: (total ms, launches)} of the launches recorded since the last reset."""
+    buf = (NvfiProfileEntry * 64)()
+    n = load().nvfi_profile_read(buf, 64, 1 if reset else 0)
+    if n < 0:
+        raise RuntimeError(f"nvfi_b200 profile_read: error {n}")
+    return {buf[i].name.decode(): (float(buf[i].ms), int(buf[i].launches)) for i in range(n)}
 
 
 _ERRORS = {-1: "NVFI_EINVAL (bad argument)", -2: "NVFI_EUNSUPPORTED (configuration outside the kernels)"}

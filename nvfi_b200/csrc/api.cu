@@ -89,7 +89,7 @@ static int launch_transpose(const float* src, float* dst, int rows, long long co
   if (!src || !dst || rows <= 0 || cols <= 0) return NVFI_EINVAL;
   dim3 block(32, 8);
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
-  k_transpose<<<grid, block, 0, st>>>(src, dst, rows, cols);
+  NVFI_LAUNCH(k_transpose, grid, block, 0, st, src, dst, rows, cols);
   return (int)cudaGetLastError();
 }
 
@@ -106,7 +106,7 @@ extern "C" int nvfi_unpack_plane(const float* src_hwc, float* dst_nchw, int r, i
   if (hw > 0x7fffffffLL) return NVFI_EUNSUPPORTED;
   dim3 block(32, 8);
   dim3 grid((unsigned)((r + 31) / 32), (unsigned)((hw + 31) / 32));
-  k_transpose<<<grid, block, 0, (cudaStream_t)stream>>>(src_hwc, dst_nchw, (int)hw, r);
+  NVFI_LAUNCH(k_transpose, grid, block, 0, (cudaStream_t)stream, src_hwc, dst_nchw, (int)hw, r);
   return (int)cudaGetLastError();
 }
 
@@ -115,8 +115,7 @@ extern "C" int nvfi_pack_linear(const float* w, const float* b, float* wt, float
   if (!w || !wt || out_dim <= 0 || in_dim <= 0 || k_pad < in_dim || n_pad < out_dim)
     return NVFI_EINVAL;
   const int n = k_pad * n_pad > n_pad ? k_pad * n_pad : n_pad;
-  k_pack_linear<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, b, wt, bias_out, out_dim,
-                                                                    in_dim, k_pad, n_pad);
+  NVFI_LAUNCH(k_pack_linear, (n + 255) / 256, 256, 0, (cudaStream_t)stream, w, b, wt, bias_out, out_dim, in_dim, k_pad, n_pad);
   return (int)cudaGetLastError();
 }
 
@@ -125,8 +124,7 @@ extern "C" int nvfi_unpack_linear(const float* wt, const float* bias_in, float* 
   if (!w || !wt || out_dim <= 0 || in_dim <= 0 || k_pad < in_dim || n_pad < out_dim)
     return NVFI_EINVAL;
   const int n = out_dim * in_dim;
-  k_unpack_linear<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(wt, bias_in, w, b, out_dim,
-                                                                      in_dim, k_pad, n_pad);
+  NVFI_LAUNCH(k_unpack_linear, (n + 255) / 256, 256, 0, (cudaStream_t)stream, wt, bias_in, w, b, out_dim, in_dim, k_pad, n_pad);
   return (int)cudaGetLastError();
 }
 
@@ -135,8 +133,7 @@ extern "C" int nvfi_raygen(const float* pose4x4, int h, int w, float focal,
                            void* stream) {
   if (!pose4x4 || !rays_o || !rays_d || h <= 0 || w <= 0 || n < 0) return NVFI_EINVAL;
   if (n == 0) return NVFI_OK;
-  k_raygen<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      pose4x4, h, w, focal, reinterpret_cast<const long long*>(pixel_ids), n, rays_o, rays_d);
+  NVFI_LAUNCH(k_raygen, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, pose4x4, h, w, focal, reinterpret_cast<const long long*>(pixel_ids), n, rays_o, rays_d);
   return (int)cudaGetLastError();
 }
 

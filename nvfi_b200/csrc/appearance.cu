@@ -358,7 +358,7 @@ extern "C" int nvfi_launch_appearance(const NvfiField* F, const NvfiRenderArgs* 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int n_batches = (int)((total + NVFI_SUBS * NVFI_THREADS - 1) / (NVFI_SUBS * NVFI_THREADS));
   const int grid = n_batches < sms * 2 ? n_batches : sms * 2;
-  k_appearance<<<grid, NVFI_THREADS, smem, st>>>(*F, *A, *B, S, total, n_batches, rows);
+  NVFI_LAUNCH(k_appearance, grid, NVFI_THREADS, smem, st, *F, *A, *B, S, total, n_batches, rows);
   return (int)cudaGetLastError();
 }
 
@@ -383,6 +383,6 @@ extern "C" int nvfi_app_feature(const NvfiField* F, const float* xyzt, int64_t n
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long n_tiles = (n + NVFI_TM - 1) / NVFI_TM;
   const int grid = (int)(n_tiles < (long long)sms * 2 ? n_tiles : (long long)sms * 2);
-  k_app_feature_points<<<grid, NVFI_THREADS, smem, st>>>(*F, xyzt, n, feat, counters, rows);
+  NVFI_LAUNCH(k_app_feature_points, grid, NVFI_THREADS, smem, st, *F, xyzt, n, feat, counters, rows);
   return (int)cudaGetLastError();
 }

@@ -503,6 +503,7 @@ __global__ void __launch_bounds__(NVFI_THREADS, 1)
   long long batch_base = 0;
   bool exhausted = false;
   int qc = 0, par = 0;
+  unsigned long long n_done = 0;
   for (;;) {
     while (qc < NVFI_TM && !exhausted) {
       if (sub == NVFI_SUBS) {
@@ -551,7 +552,10 @@ __global__ void __launch_bounds__(NVFI_THREADS, 1)
     }
     __syncthreads();
     app_bwd_tile(F, A, B, D, T, n, At, Gt, wS, ws);
+    n_done += n;
   }
+  if (tid == 0 && n_done)  // samples back-propagated (bench.py's algorithmic flop count)
+    atomicAdd(reinterpret_cast<unsigned long long*>(B.counters + 8), n_done);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -697,6 +701,7 @@ __global__ void __launch_bounds__(NVFI_THREADS, 1)
   long long batch_base = 0;
   bool exhausted = false;
   int qc = 0, par = 0;
+  unsigned long long n_done = 0;
   for (;;) {
     while (qc < NVFI_TM && !exhausted) {
       if (sub == NVFI_SUBS) {
@@ -735,6 +740,7 @@ __global__ void __launch_bounds__(NVFI_THREADS, 1)
     const int n = min(NVFI_TM, qc);
     const int start = qc - n;
     qc = start;
+    n_done += n;
     // ---- load the tile: start position (sampler recompute) and upstream gradient
     if (tid < NVFI_TM) {
       const bool live = tid < n;
@@ -911,6 +917,8 @@ __global__ void __launch_bounds__(NVFI_THREADS, 1)
       __syncthreads();
     }
   }
+  if (tid == 0 && n_done)
+    atomicAdd(reinterpret_cast<unsigned long long*>(B.counters + 10), n_done);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1007,7 +1015,7 @@ extern "C" int nvfi_render_backward(const NvfiField* F, const NvfiRenderArgs* A,
                                         (int)smem));
       attr = smem;
     }
-    k_march_bwd<<<(unsigned)((A->n_rays + 7) / 8), 256, smem, st>>>(*F, *A, *B, *D, S, s_pad);
+    NVFI_LAUNCH(k_march_bwd, (unsigned)((A->n_rays + 7) / 8), 256, smem, st, *F, *A, *B, *D, S, s_pad);
     NVFI_CUDA_OK(cudaGetLastError());
   }
   // 2. appearance
@@ -1028,26 +1036,21 @@ extern "C" int nvfi_render_backward(const NvfiField* F, const NvfiRenderArgs* A,
       attr = true;
     }
     const int grid = n_batches < sms ? n_batches : sms;
-    k_app_bwd<<<grid, NVFI_THREADS, smem, st>>>(*F, *A, *B, *D, S, total, n_batches);
+    NVFI_LAUNCH(k_app_bwd, grid, NVFI_THREADS, smem, st, *F, *A, *B, *D, S, total, n_batches);
     NVFI_CUDA_OK(cudaGetLastError());
     if (F->shading_mode == NVFI_SHADING_MLP_PE) {
-      k_reduce_outer<<<(8 * 2048 + 255) / 256, 256, 0, st>>>(D->workspace, grid, AW_W0, 8,
-                                                             D->g_render_w[0]);
-      k_reduce_outer<<<(8 * 2048 + 255) / 256, 256, 0, st>>>(D->workspace, grid, AW_W1, 8,
-                                                             D->g_render_w[1]);
-      k_reduce_small<<<4, 256, 0, st>>>(D->workspace, grid, AW_W2, F->render_mlp[2].n_pad,
-                                        D->g_render_w[2]);
-      k_reduce_vec<<<1, 128, 0, st>>>(D->workspace, grid, AW_B(0), 128, D->g_render_b[0]);
-      k_reduce_vec<<<1, 128, 0, st>>>(D->workspace, grid, AW_B(1), 128, D->g_render_b[1]);
-      k_reduce_vec<<<1, 128, 0, st>>>(D->workspace, grid, AW_B(2), F->render_mlp[2].n_pad,
-                                      D->g_render_b[2]);
+      NVFI_LAUNCH(k_reduce_outer, (8 * 2048 + 255) / 256, 256, 0, st, D->workspace, grid, AW_W0, 8, D->g_render_w[0]);
+      NVFI_LAUNCH(k_reduce_outer, (8 * 2048 + 255) / 256, 256, 0, st, D->workspace, grid, AW_W1, 8, D->g_render_w[1]);
+      NVFI_LAUNCH(k_reduce_small, 4, 256, 0, st, D->workspace, grid, AW_W2, F->render_mlp[2].n_pad, D->g_render_w[2]);
+      NVFI_LAUNCH(k_reduce_vec, 1, 128, 0, st, D->workspace, grid, AW_B(0), 128, D->g_render_b[0]);
+      NVFI_LAUNCH(k_reduce_vec, 1, 128, 0, st, D->workspace, grid, AW_B(1), 128, D->g_render_b[1]);
+      NVFI_LAUNCH(k_reduce_vec, 1, 128, 0, st, D->workspace, grid, AW_B(2), F->render_mlp[2].n_pad, D->g_render_b[2]);
     }
-    k_reduce_basis<<<(F->app_dim * F->ra + 255) / 256, 256, 0, st>>>(
-        D->workspace, grid, AW_BASIS, F->app_dim, F->ra, F->basis_mat.n_pad, D->g_basis_mat);
+    NVFI_LAUNCH(k_reduce_basis, (F->app_dim * F->ra + 255) / 256, 256, 0, st, D->workspace, grid, AW_BASIS, F->app_dim, F->ra, F->basis_mat.n_pad, D->g_basis_mat);
     NVFI_CUDA_OK(cudaGetLastError());
   }
   // 3. density planes + positions
-  k_density_bwd<<<(unsigned)((A->n_rays + 7) / 8), 256, 0, st>>>(*F, *A, *B, *D, S);
+  NVFI_LAUNCH(k_density_bwd, (unsigned)((A->n_rays + 7) / 8), 256, 0, st, *F, *A, *B, *D, S);
   NVFI_CUDA_OK(cudaGetLastError());
   // 4. velocity net
   if (A->advect) {
@@ -1072,17 +1075,15 @@ extern "C" int nvfi_render_backward(const NvfiField* F, const NvfiRenderArgs* A,
       attr = true;
     }
     const int grid = n_batches < sms ? n_batches : sms;
-    k_advect_bwd<<<grid, NVFI_THREADS, smem, st>>>(*F, *A, *B, *D, S, total, n_batches);
+    NVFI_LAUNCH(k_advect_bwd, grid, NVFI_THREADS, smem, st, *F, *A, *B, *D, S, total, n_batches);
     NVFI_CUDA_OK(cudaGetLastError());
-    k_reduce_outer<<<(2 * 2048 + 255) / 256, 256, 0, st>>>(D->workspace, grid, VW_W0, 2,
-                                                           D->g_vel_w[0]);
+    NVFI_LAUNCH(k_reduce_outer, (2 * 2048 + 255) / 256, 256, 0, st, D->workspace, grid, VW_W0, 2, D->g_vel_w[0]);
     for (int l = 1; l <= 4; ++l)
-      k_reduce_outer<<<(8 * 2048 + 255) / 256, 256, 0, st>>>(D->workspace, grid, VW_W(l), 8,
-                                                             D->g_vel_w[l]);
-    k_reduce_small<<<4, 256, 0, st>>>(D->workspace, grid, VW_W5, 8, D->g_vel_w[5]);
+      NVFI_LAUNCH(k_reduce_outer, (8 * 2048 + 255) / 256, 256, 0, st, D->workspace, grid, VW_W(l), 8, D->g_vel_w[l]);
+    NVFI_LAUNCH(k_reduce_small, 4, 256, 0, st, D->workspace, grid, VW_W5, 8, D->g_vel_w[5]);
     for (int l = 0; l < 5; ++l)
-      k_reduce_vec<<<1, 128, 0, st>>>(D->workspace, grid, VW_B(l), 128, D->g_vel_b[l]);
-    k_reduce_vec<<<1, 128, 0, st>>>(D->workspace, grid, VW_B(5), 8, D->g_vel_b[5]);
+      NVFI_LAUNCH(k_reduce_vec, 1, 128, 0, st, D->workspace, grid, VW_B(l), 128, D->g_vel_b[l]);
+    NVFI_LAUNCH(k_reduce_vec, 1, 128, 0, st, D->workspace, grid, VW_B(5), 8, D->g_vel_b[5]);
     NVFI_CUDA_OK(cudaGetLastError());
   }
   return NVFI_OK;

@@ -198,7 +198,7 @@ extern "C" int nvfi_launch_march(const NvfiField* F, const NvfiRenderArgs* A,
     attr_smem = smem;
   }
   const long long grid = (A->n_rays + MARCH_WARPS - 1) / MARCH_WARPS;
-  k_march<<<(unsigned)grid, MARCH_WARPS * 32, smem, st>>>(*F, *A, *B, S, s_pad);
+  NVFI_LAUNCH(k_march, (unsigned)grid, MARCH_WARPS * 32, smem, st, *F, *A, *B, S, s_pad);
   return (int)cudaGetLastError();
 }
 
@@ -206,7 +206,7 @@ extern "C" int nvfi_launch_composite(const NvfiField* F, const NvfiRenderArgs* A
                                      const NvfiRenderBuffers* B, cudaStream_t st) {
   if (A->n_rays <= 0) return NVFI_OK;
   const long long grid = (A->n_rays + 7) / 8;
-  k_composite<<<(unsigned)grid, 256, 0, st>>>(*F, *A, *B, F->n_samples);
+  NVFI_LAUNCH(k_composite, (unsigned)grid, 256, 0, st, *F, *A, *B, F->n_samples);
   return (int)cudaGetLastError();
 }
 
@@ -217,7 +217,7 @@ extern "C" int nvfi_density_feature(const NvfiField* F, const float* xyzt, int64
   const long long groups = (n + 3) / 4;  // warps needed
   long long grid = (groups + 7) / 8;
   if (grid > 148 * 64) grid = 148 * 64;
-  k_density_points<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(*F, xyzt, n, feat, nullptr);
+  NVFI_LAUNCH(k_density_points, (unsigned)grid, 256, 0, (cudaStream_t)stream, *F, xyzt, n, feat, nullptr);
   return (int)cudaGetLastError();
 }
 
@@ -228,7 +228,7 @@ extern "C" int nvfi_density_sigma(const NvfiField* F, const float* xyzt, int64_t
   const long long groups = (n + 3) / 4;
   long long grid = (groups + 7) / 8;
   if (grid > 148 * 64) grid = 148 * 64;
-  k_density_points<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(*F, xyzt, n, nullptr, sigma);
+  NVFI_LAUNCH(k_density_points, (unsigned)grid, 256, 0, (cudaStream_t)stream, *F, xyzt, n, nullptr, sigma);
   return (int)cudaGetLastError();
 }
 
@@ -238,6 +238,6 @@ extern "C" int nvfi_feature2density(const NvfiField* F, const float* feat, int64
   if (n == 0) return NVFI_OK;
   long long grid = (n + 255) / 256;
   if (grid > 148 * 32) grid = 148 * 32;
-  k_feature2density<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(*F, feat, n, sigma);
+  NVFI_LAUNCH(k_feature2density, (unsigned)grid, 256, 0, (cudaStream_t)stream, *F, feat, n, sigma);
   return (int)cudaGetLastError();
 }

@@ -12,6 +12,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdio>
 
 #include "nvfi_b200.h"
 
@@ -32,7 +33,22 @@
     if (_e != cudaSuccess) return (int)_e;         \
   } while (0)
 
+#define NVFI_LAUNCH(kernel, grid, block, smem, st, ...)       \
+  do {                                                         \
+    nvfi::ProfScope ps_(#kernel, (st));                        \
+    kernel<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);    \
+  } while (0)
+
 namespace nvfi {
+
+// Host side: counts a kernel launch and, when profiling is on, times it (prof.cu).
+// Used through NVFI_LAUNCH.
+struct ProfScope {
+  ProfScope(const char* name, cudaStream_t st);
+  ~ProfScope();
+  cudaStream_t st_;
+  int idx_;
+};
 
 // ------------------------------------------------------------------ scalar helpers
 __device__ __forceinline__ float softplus_f(float x) {  // F.softplus(beta=1, threshold=20)

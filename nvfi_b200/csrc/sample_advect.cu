@@ -304,13 +304,12 @@ extern "C" int nvfi_launch_sample_advect(const NvfiField* F, const NvfiRenderArg
   if (total <= 0) return NVFI_OK;
   if (total >= (1ll << 31)) return NVFI_EUNSUPPORTED;  // queue indices are int32
   const int n_chunks = (int)((A->n_rays + A->ray_chunk - 1) / A->ray_chunk);
-  k_chunk_inside<<<n_chunks, 256, 0, st>>>(*F, A->rays_o, A->n_rays, A->ray_chunk,
-                                           B->chunk_inside);
+  NVFI_LAUNCH(k_chunk_inside, n_chunks, 256, 0, st, *F, A->rays_o, A->n_rays, A->ray_chunk, B->chunk_inside);
   NVFI_CUDA_OK(cudaGetLastError());
   if (!A->advect) {
     const long long blocks = (total + 255) / 256;
     const int grid = (int)(blocks < (long long)num_sms() * 16 ? blocks : (long long)num_sms() * 16);
-    k_sample_only<<<grid, 256, 0, st>>>(*F, *A, *B, S, total);
+    NVFI_LAUNCH(k_sample_only, grid, 256, 0, st, *F, *A, *B, S, total);
     return (int)cudaGetLastError();
   }
   const size_t smem = sizeof(SampleAdvectSmem);
@@ -322,7 +321,7 @@ extern "C" int nvfi_launch_sample_advect(const NvfiField* F, const NvfiRenderArg
   }
   const int n_batches = (int)((total + NVFI_SUBS * NVFI_THREADS - 1) / (NVFI_SUBS * NVFI_THREADS));
   const int grid = min(n_batches, num_sms() * 2);
-  k_sample_advect<<<grid, NVFI_THREADS, smem, st>>>(*F, *A, *B, S, total, n_batches);
+  NVFI_LAUNCH(k_sample_advect, grid, NVFI_THREADS, smem, st, *F, *A, *B, S, total, n_batches);
   return (int)cudaGetLastError();
 }
 
@@ -342,7 +341,7 @@ extern "C" int nvfi_integrate_pos(const NvfiField* F, const float* x, const floa
   NVFI_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(int32_t), st));
   const long long n_tiles = (n + NVFI_TM - 1) / NVFI_TM;
   const int grid = (int)(n_tiles < (long long)num_sms() * 2 ? n_tiles : (long long)num_sms() * 2);
-  k_integrate_pos<<<grid, NVFI_THREADS, smem, st>>>(*F, x, t, base, n, out, counters);
+  NVFI_LAUNCH(k_integrate_pos, grid, NVFI_THREADS, smem, st, *F, x, t, base, n, out, counters);
   return (int)cudaGetLastError();
 }
 
@@ -361,6 +360,6 @@ extern "C" int nvfi_velocity(const NvfiField* F, const float* xyzt, int64_t n, i
   NVFI_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(int32_t), st));
   const long long n_tiles = (n + NVFI_TM - 1) / NVFI_TM;
   const int grid = (int)(n_tiles < (long long)num_sms() * 2 ? n_tiles : (long long)num_sms() * 2);
-  k_velocity<<<grid, NVFI_THREADS, smem, st>>>(*F, xyzt, n, full, out, counters);
+  NVFI_LAUNCH(k_velocity, grid, NVFI_THREADS, smem, st, *F, xyzt, n, full, out, counters);
   return (int)cudaGetLastError();
 }

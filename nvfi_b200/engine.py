@@ -376,6 +376,7 @@ def render_forward(binding: FieldBinding, rays_o: torch.Tensor, rays_d: torch.Te
 
 
 DEBUG_KEEP: Optional[dict] = None   # tests may set this to a dict to receive backward intermediates
+LAST_BWD_COUNTERS: Optional[torch.Tensor] = None   # int32[16] of the most recent render_backward
 
 
 def render_backward(binding: FieldBinding, out: RenderOutputs, g_rgb, g_depth, g_acc, g_w,
@@ -433,6 +434,8 @@ def render_backward(binding: FieldBinding, out: RenderOutputs, g_rgb, g_depth, g
     d.workspace, d.workspace_bytes = ws.data_ptr(), ws_bytes
     L.check(lib.nvfi_render_backward(C.byref(s), C.byref(a), C.byref(b), C.byref(d), _stream()),
             "render_backward")
+    global LAST_BWD_COUNTERS
+    LAST_BWD_COUNTERS = out.counters
     if DEBUG_KEEP is not None:
         DEBUG_KEEP.update(g_sigma=g_sig, g_x_adv=g_x, g_rgb_eff=g_eff, fwd=out)
     grads: List[Optional[torch.Tensor]] = []

@@ -1,0 +1,122 @@
+"""Ray sharding across the GPUs of one box.
+
+The reference is single-process (no torch.distributed anywhere); rays are independent, so
+the B200 build adds plain data parallelism: one process per GPU, parameters replicated, a
+contiguous block of rays per rank and ONE collective per step —
+
+  * eval:  every rank renders its block of the frame, then one all-gather of the
+           (rgb, depth, acc[, mask]) slabs (``gather_frame``);
+  * train: every rank back-propagates its block, then one all-reduce(sum) over a single
+           flat FP32 buffer holding every parameter gradient plus the loss numerator and
+           the ray count (``allreduce_grads``), so the result equals the single-GPU
+           mean-reduced loss / gradient.
+
+The only cross-ray coupling in the reference is the chunk-global inside-box predicate of
+``sample_ray`` (models/tensorf_base.py:294): shards are cut at multiples of the reference
+chunk size (``ray_chunk``), so every reference chunk lives on exactly one rank and the
+predicate is evaluated on the same set of rays as in the single-process run.
+
+Works with any initialised ``torch.distributed`` backend (NCCL on the GPUs; the CPU tests
+use gloo).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n_rays: int, rank: int, world_size: int, ray_chunk: int = 2048) -> Tuple[int, int]:
+    """[begin, end) of the rays rank ``rank`` renders: contiguous, chunk-aligned, sizes
+    differing by at most one chunk, the union covering [0, n_rays) exactly once."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank/world_size {rank}/{world_size}")
+    if n_rays < 0 or ray_chunk <= 0:
+        raise ValueError("n_rays must be >= 0 and ray_chunk > 0")
+    n_chunks = (n_rays + ray_chunk - 1) // ray_chunk
+    base, extra = divmod(n_chunks, world_size)
+    c0 = rank * base + min(rank, extra)
+    c1 = c0 + base + (1 if rank < extra else 0)
+    return min(c0 * ray_chunk, n_rays), min(c1 * ray_chunk, n_rays)
+
+
+def shard_rays(tensors: Sequence[Optional[torch.Tensor]], rank: int, world_size: int,
+               ray_chunk: int = 2048) -> List[Optional[torch.Tensor]]:
+    """Slice per-ray tensors (first dim = rays) to this rank's block."""
+    n = next(t.shape[0] for t in tensors if t is not None)
+    b, e = shard_bounds(n, rank, world_size, ray_chunk)
+    return [None if t is None else t[b:e] for t in tensors]
+
+
+def gather_frame(parts: Sequence[torch.Tensor], n_rays: int, ray_chunk: int = 2048,
+                 group=None) -> List[torch.Tensor]:
+    """Eval: all-gather the per-rank slabs of per-ray outputs into full-frame tensors.
+
+    ``parts`` are this rank's (n_local, c_i) / (n_local,) outputs.  They are packed into one
+    (n_local, sum c_i) buffer so that a frame costs exactly one collective."""
+    rank, ws = world()
+    if ws == 1:
+        return [p for p in parts]
+    widths = [1 if p.dim() == 1 else p.shape[1] for p in parts]
+    n_local = parts[0].shape[0]
+    packed = torch.cat([p.reshape(n_local, -1).float() for p in parts], dim=1).contiguous()
+    sizes = [shard_bounds(n_rays, r, ws, ray_chunk) for r in range(ws)]
+    max_n = max(e - b for b, e in sizes)
+    if n_local < max_n:   # all_gather wants equal shapes: pad the short slabs
+        pad = torch.zeros(max_n - n_local, packed.shape[1], device=packed.device, dtype=packed.dtype)
+        packed = torch.cat([packed, pad], 0)
+    out = torch.empty(ws * max_n, packed.shape[1], device=packed.device, dtype=packed.dtype)
+    dist.all_gather_into_tensor(out, packed, group=group)
+    full = torch.cat([out[r * max_n: r * max_n + (e - b)] for r, (b, e) in enumerate(sizes)], 0)
+    res, c = [], 0
+    for p, w in zip(parts, widths):
+        col = full[:, c:c + w]
+        res.append(col.reshape(n_rays) if p.dim() == 1 else col.reshape(n_rays, w))
+        c += w
+    return res
+
+
+def allreduce_grads(params: Iterable[torch.nn.Parameter], extras: Optional[torch.Tensor] = None,
+                    group=None, average: bool = False) -> Optional[torch.Tensor]:
+    """Train: ONE all-reduce(sum) over [all param grads || extras] in a flat FP32 buffer.
+
+    ``extras`` (1-D tensor) carries scalars that must be summed across ranks as well (loss
+    numerators, ray / point counts); the reduced copy is returned.  Parameters whose grad is
+    None are skipped and stay None, as in the single-process run (the fused backward yields
+    gradients for the same parameter set on every rank whatever its rays hit, so the flat
+    buffers line up).  With ``average`` the
+    gradients are divided by the world size afterwards (use it when every rank's loss is
+    already a mean over its own, equally sized block)."""
+    rank, ws = world()
+    plist = [p for p in params if p.requires_grad and p.grad is not None]
+    if ws == 1:
+        return extras
+    dev = plist[0].device if plist else extras.device
+    numel = sum(p.numel() for p in plist) + (extras.numel() if extras is not None else 0)
+    flat = torch.zeros(numel, device=dev, dtype=torch.float32)
+    off = 0
+    for p in plist:
+        n = p.numel()
+        flat[off:off + n].copy_(p.grad.reshape(-1))
+        off += n
+    if extras is not None:
+        flat[off:].copy_(extras.reshape(-1).float())
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    scale = 1.0 / ws if average else 1.0
+    for p in plist:
+        n = p.numel()
+        g = flat[off:off + n].view_as(p)
+        if average:
+            g = g * scale
+        p.grad.copy_(g)
+        off += n
+    return flat[off:].clone() if extras is not None else None
