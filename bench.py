@@ -228,9 +228,12 @@ def run_gpu(args):
     assert field.nSamples == 192, field.nSamples
     nv.requires_grad_(True)
     renderer = M.Renderer(nv, 0, 0, RAY_CHUNK)
-    n = H * W
     # weak scaling: every rank renders its own camera of the same scene
     o_h, d_h = frame_rays(H, W, theta=30.0 + 9.0 * rank)
+    if args.rows != H:      # profiling aid: a horizontal band through the middle of the frame
+        r0 = (H - args.rows) // 2
+        o_h, d_h = o_h[r0 * W:(r0 + args.rows) * W].contiguous(), d_h[r0 * W:(r0 + args.rows) * W].contiguous()
+    n = o_h.shape[0]
     gen = torch.Generator().manual_seed(1000 + rank)
     target_h = torch.rand(n, 3, generator=gen)
     jitter_h = torch.rand(n, 1, generator=gen)
@@ -370,6 +373,8 @@ def run_gpu(args):
             tt, rr, k = leg.run(args.cpu_budget, 8)
             line["cpu_baseline"] = {"value": rr / tt, "unit": UNIT, "cores": leg.cores, "kind": "port",
                                     "sample": cpu_sample_desc(k)}
+        if args.rows != H:
+            line["invalid_for_bench"] = f"profiling run on {args.rows} of {H} rows"
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier(device_ids=[local_rank])
@@ -383,6 +388,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="nvfi_b200", choices=["nvfi_b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--rows", type=int, default=H,
+                    help="PROFILING ONLY: render the first ROWS rows of the 800x800 frame (ncu replays are "
+                         "slow on the 6 GB full-frame working set); the line is marked invalid_for_bench")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()
     if args.impl == "reference":

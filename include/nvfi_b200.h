@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NVFI_ABI_VERSION 5
+#define NVFI_ABI_VERSION 7
 
 /* error codes */
 #define NVFI_OK 0
@@ -44,6 +44,11 @@ extern "C" {
 
 #define NVFI_SHADING_MLP_PE 0 /* models/tensorf_base.py:67-98 */
 #define NVFI_SHADING_SH 1     /* models/tensorf_model_utils.py:292-296 */
+
+/* arithmetic of the velocity-MLP GEMMs (nvfi_set_mlp_mode) */
+#define NVFI_MLP_FP32_SIMT 0 /* FP32 FMA tile GEMM (verification path) */
+#define NVFI_MLP_TF32X3 1    /* tcgen05 TF32 tensor cores, 3-term split: FP32-grade (default) */
+#define NVFI_MLP_TF32 2      /* tcgen05 single TF32 pass: fastest, ~1e-3 relative */
 
 #define NVFI_GATE_AABB 0 /* VelocityAABB,    models/velocity_field.py:21-33 */
 #define NVFI_GATE_SUR 1  /* VelocityAABBSur, models/velocity_field.py:36-51 */
@@ -61,8 +66,14 @@ typedef struct NvfiLinear {
   const float* bias;
   const float* w_rows; /* (128, k_pad) row-major = W zero padded, for the input-gradient GEMM
                           of the backward pass; NULL when the layer is never differentiated */
+  const float* umma;   /* tensor-core image produced by nvfi_pack_linear_umma (velocity nets):
+                          per 32-wide K block the TF32 "hi" slab [umma_rows][32] followed by the
+                          "lo" (residual) slab, both K-major with the 128-byte swizzle; NULL when
+                          the layer only runs on the FP32 SIMT path */
   int32_t in_dim, out_dim; /* logical sizes */
   int32_t k_pad, n_pad;    /* padded sizes: k_pad % 32 == 0, n_pad % 4 == 0 */
+  int32_t umma_rows;       /* rows (N) of the image: 128 for hidden layers, 16 for a narrow head */
+  int32_t reserved_;
 } NvfiLinear;
 
 /* Everything the render path reads.  Mirrors the attributes of
@@ -177,6 +188,18 @@ typedef struct NvfiRenderGrads {
   int64_t workspace_bytes; /* >= nvfi_backward_workspace_bytes() */
 } NvfiRenderGrads;
 
+/* Gradient accumulators of nvfi_pde_loss, in the packed layouts of NvfiLinear.wt / bias
+ * (convert with nvfi_unpack_linear).  All g_* must be zero-initialised by the caller. */
+typedef struct NvfiPdeGrads {
+  float* g_vel_w[NVFI_VEL_LAYERS]; /* weight_net   (SiLU net: through value AND Jacobian) */
+  float* g_vel_b[NVFI_VEL_LAYERS];
+  float* g_acc_w[NVFI_VEL_LAYERS]; /* a_weight_net (ReLU twin: through the value of a only) */
+  float* g_acc_b[NVFI_VEL_LAYERS];
+  float* g_acc_pts;                /* scratch (n, 3): dL/da per point */
+  float* workspace;                /* scratch, >= nvfi_backward_workspace_bytes() */
+  int64_t workspace_bytes;
+} NvfiPdeGrads;
+
 /* ---- library info --------------------------------------------------------------- */
 int nvfi_abi_version(void);
 /* Bytes of `workspace` scratch nvfi_render_backward needs on the current device. */
@@ -197,6 +220,12 @@ int nvfi_profile_enable(int on);
 /* Fills up to `cap` entries; returns the number filled (< 0 on error).  reset != 0 clears. */
 int nvfi_profile_read(NvfiProfileEntry* out, int cap, int reset);
 
+/* Selects the arithmetic of the velocity-MLP GEMMs for subsequent calls (process-wide; the
+ * default is NVFI_MLP_TF32X3, or the value of the environment variable NVFI_MLP_MODE =
+ * simt | tf32x3 | tf32 at load).  Returns the previous mode, or NVFI_EINVAL. */
+int nvfi_set_mlp_mode(int mode);
+int nvfi_get_mlp_mode(void);
+
 /* ---- layout packing ----------------------------------------------------------------
  * Replaces nothing in the reference (it reads NCHW through F.grid_sample,
  * models/tensorf_keyframe.py:259-264); the packed layout makes one bilinear corner a
@@ -209,6 +238,11 @@ int nvfi_pack_linear(const float* w, const float* b, float* wt, float* bias_out,
                      int in_dim, int k_pad, int n_pad, void* stream);
 int nvfi_unpack_linear(const float* wt, const float* bias_in, float* w, float* b, int out_dim,
                        int in_dim, int k_pad, int n_pad, void* stream);
+
+/* nn.Linear (out,in) -> tensor-core image (see NvfiLinear.umma): dst holds
+ * (k_pad / 32) * 2 * n_rows * 32 floats. */
+int nvfi_pack_linear_umma(const float* w, float* dst, int out_dim, int in_dim, int n_rows, int k_pad,
+                          void* stream);
 
 /* ---- rays ----------------------------------------------------------------------------
  * Camera.get_ray_bundle for selected pixels (models/camera.py:112-138):
@@ -256,6 +290,21 @@ int nvfi_app_feature(const NvfiField* field, const float* xyzt, int64_t n, float
 /* VelBasis.forward / get_vel and the gated VelocityAABB(.Sur) (models/velocity_field.py):
  * out (n, 6) = [v, a] when full != 0, else (n, 3) gated velocity. */
 int nvfi_velocity(const NvfiField* field, const float* xyzt, int64_t n, int32_t full, float* out,
+                  int32_t* counters, void* stream);
+
+/* ---- PDE loss (NVFi.get_vel_loss, models/nvfi.py:69-84) ----------------------------------
+ * On the n occupied points xyzt (n,4) (normalised x, raw t; the occupancy filter of
+ * models/nvfi.py:50-64 is nvfi_integrate_pos + nvfi_density_sigma on the host side):
+ *   J = d VelBasis.forward / d(x,y,z,t)  (rows 0-2),  div = tr J[:, :3],
+ *   transport = J[:, :3] v + J[:, 3] - a,
+ *   loss = 5 mean(div^2) + 0.1 mean(transport^2).
+ * `va` (n,6) = VelBasis.forward(xyzt) from nvfi_velocity(full = 1).  loss_sums receives
+ * [sum div^2, sum transport^2] (double[2], device); the loss is 5 s0 / n + 0.1 s1 / (3 n).
+ * With `grads` != NULL the gradients of that loss w.r.t. both nets are accumulated
+ * (hand-written reverse pass of the forward-mode Jacobian, second order through SiLU).
+ * grads->workspace is needed in both cases (per-CTA activation stash). */
+int nvfi_pde_loss(const NvfiField* field, const float* xyzt, const float* va, int64_t n,
+                  double* loss_sums, const NvfiPdeGrads* grads, int32_t want_grad,
                   int32_t* counters, void* stream);
 
 #ifdef __cplusplus

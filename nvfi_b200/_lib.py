@@ -12,11 +12,12 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnvfi_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 7
 VEL_LAYERS = 6
 MAX_MASK_LAYERS = 8
 
 ACT_SOFTPLUS, ACT_RELU, ACT_RELU_ABS = 0, 1, 2
+MLP_FP32_SIMT, MLP_TF32X3, MLP_TF32 = 0, 1, 2
 SHADING_MLP_PE, SHADING_SH = 0, 1
 GATE_AABB, GATE_SUR = 0, 1
 
@@ -27,8 +28,9 @@ P3 = C.c_void_p * 3
 
 
 class NvfiLinear(C.Structure):
-    _fields_ = [("wt", C.c_void_p), ("bias", C.c_void_p), ("w_rows", C.c_void_p), ("in_dim", C.c_int32),
-                ("out_dim", C.c_int32), ("k_pad", C.c_int32), ("n_pad", C.c_int32)]
+    _fields_ = [("wt", C.c_void_p), ("bias", C.c_void_p), ("w_rows", C.c_void_p), ("umma", C.c_void_p),
+                ("in_dim", C.c_int32), ("out_dim", C.c_int32), ("k_pad", C.c_int32), ("n_pad", C.c_int32),
+                ("umma_rows", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class NvfiField(C.Structure):
@@ -82,6 +84,14 @@ class NvfiRenderGrads(C.Structure):
     ]
 
 
+class NvfiPdeGrads(C.Structure):
+    _fields_ = [
+        ("g_vel_w", C.c_void_p * VEL_LAYERS), ("g_vel_b", C.c_void_p * VEL_LAYERS),
+        ("g_acc_w", C.c_void_p * VEL_LAYERS), ("g_acc_b", C.c_void_p * VEL_LAYERS),
+        ("g_acc_pts", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
 class NvfiProfileEntry(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("ms", C.c_double), ("launches", C.c_int64)]
 
@@ -96,6 +106,9 @@ SIGNATURES = {
     "nvfi_launch_count": (_i64, []),
     "nvfi_profile_enable": (_i, [_i]),
     "nvfi_profile_read": (_i, [C.POINTER(NvfiProfileEntry), _i, _i]),
+    "nvfi_set_mlp_mode": (_i, [_i]),
+    "nvfi_get_mlp_mode": (_i, []),
+    "nvfi_pack_linear_umma": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "nvfi_pack_plane": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "nvfi_unpack_plane": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "nvfi_pack_linear": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -114,6 +127,7 @@ SIGNATURES = {
     "nvfi_feature2density": (_i, [C.POINTER(NvfiField), _vp, _i64, _vp, _vp]),
     "nvfi_app_feature": (_i, [C.POINTER(NvfiField), _vp, _i64, _vp, _vp, _vp]),
     "nvfi_velocity": (_i, [C.POINTER(NvfiField), _vp, _i64, _i, _vp, _vp, _vp]),
+    "nvfi_pde_loss": (_i, [C.POINTER(NvfiField), _vp, _vp, _i64, _vp, C.POINTER(NvfiPdeGrads), _i, _vp, _vp]),
 }
 
 

@@ -1,6 +1,9 @@
 // C-ABI entry points (include/nvfi_b200.h): layout packing, ray generation and the
 // forward-render orchestration.  Every function validates its arguments, enqueues
 // kernels on the caller's stream and returns an error code; nothing here touches torch.
+#include <cstdlib>
+#include <cstring>
+
 #include "nvfi_common.cuh"
 
 extern "C" int nvfi_launch_sample_advect(const NvfiField*, const NvfiRenderArgs*,
@@ -54,6 +57,28 @@ __global__ void k_unpack_linear(const float* __restrict__ wt, const float* __res
     w[i] = wt[k * n_pad + n];
   }
   if (b && bi && i < out_dim) b[i] = bi[i];
+}
+
+// nn.Linear (out,in) -> tensor-core image: per 32-wide K block the TF32-rounded "hi" slab
+// [n_rows][32] then the residual "lo" slab, rows of 128 bytes whose 16-byte chunks are
+// XOR-swizzled with (row & 7) (canonical K-major SWIZZLE_128B operand layout of tcgen05.mma).
+__global__ void k_pack_linear_umma(const float* __restrict__ w, float* __restrict__ dst, int out_dim,
+                                   int in_dim, int n_rows, int k_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_kb = n_rows * 32;
+  if (i >= (k_pad / 32) * per_kb) return;
+  const int kb = i / per_kb, r = i - kb * per_kb;
+  const int n = r >> 5, kk = r & 31;
+  const int k = kb * 32 + kk;
+  const float v = (n < out_dim && k < in_dim) ? w[n * in_dim + k] : 0.f;
+  uint32_t hb;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+  const float hi = __uint_as_float(hb);
+  const float lo = v - hi;
+  const int off = n * 32 + (((kk >> 2) ^ (n & 7)) << 2) + (kk & 3);
+  float* blk = dst + (size_t)kb * 2 * per_kb;
+  blk[off] = hi;
+  blk[per_kb + off] = lo;
 }
 
 // Camera.get_ray_bundle (models/camera.py:112-138), per selected pixel.
@@ -126,6 +151,37 @@ extern "C" int nvfi_unpack_linear(const float* wt, const float* bias_in, float* 
   const int n = out_dim * in_dim;
   NVFI_LAUNCH(k_unpack_linear, (n + 255) / 256, 256, 0, (cudaStream_t)stream, wt, bias_in, w, b, out_dim, in_dim, k_pad, n_pad);
   return (int)cudaGetLastError();
+}
+
+extern "C" int nvfi_pack_linear_umma(const float* w, float* dst, int out_dim, int in_dim, int n_rows,
+                                     int k_pad, void* stream) {
+  if (!w || !dst || out_dim <= 0 || in_dim <= 0 || n_rows < out_dim || k_pad < in_dim ||
+      (k_pad & 31) || (n_rows & 7))
+    return NVFI_EINVAL;
+  const int n = (k_pad / 32) * n_rows * 32;
+  NVFI_LAUNCH(k_pack_linear_umma, (n + 255) / 256, 256, 0, (cudaStream_t)stream, w, dst, out_dim,
+              in_dim, n_rows, k_pad);
+  return (int)cudaGetLastError();
+}
+
+static int g_mlp_mode = -1;
+extern "C" int nvfi_get_mlp_mode(void) {
+  if (g_mlp_mode < 0) {
+    g_mlp_mode = NVFI_MLP_TF32X3;
+    const char* e = getenv("NVFI_MLP_MODE");
+    if (e) {
+      if (!strcmp(e, "simt")) g_mlp_mode = NVFI_MLP_FP32_SIMT;
+      else if (!strcmp(e, "tf32")) g_mlp_mode = NVFI_MLP_TF32;
+      else if (!strcmp(e, "tf32x3")) g_mlp_mode = NVFI_MLP_TF32X3;
+    }
+  }
+  return g_mlp_mode;
+}
+extern "C" int nvfi_set_mlp_mode(int mode) {
+  if (mode < NVFI_MLP_FP32_SIMT || mode > NVFI_MLP_TF32) return NVFI_EINVAL;
+  const int prev = nvfi_get_mlp_mode();
+  g_mlp_mode = mode;
+  return prev;
 }
 
 extern "C" int nvfi_raygen(const float* pose4x4, int h, int w, float focal,

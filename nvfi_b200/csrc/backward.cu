@@ -12,33 +12,6 @@
 namespace nvfi {
 
 // ---------------------------------------------------------------------------------------
-// per-CTA workspace layouts (float offsets)
-// ---------------------------------------------------------------------------------------
-// velocity (k_advect_bwd)
-#define VW_W0 0                                 // 32 x 128 (tile_outer layout, KI = 2)
-#define VW_W(l) (4096 + ((l) - 1) * 16384)      // l = 1..4, 128 x 128 (KI = 8)
-#define VW_W5 (4096 + 4 * 16384)                // small layout, 1024
-#define VW_B(l) (VW_W5 + 1024 + (l) * 128)      // l = 0..5 (last uses 8)
-#define VW_PART_F (VW_W5 + 1024 + 6 * 128)      // floats of partials
-#define VW_STASH (VW_PART_F)                    // [2 evals][5 layers][STASH_F]
-#define VW_XSTEPS (VW_STASH + 10 * STASH_F)     // [32 steps][3][128]
-#define VW_TOTAL (VW_XSTEPS + 32 * 3 * NVFI_TM)
-// appearance (k_app_bwd)
-#define AW_W0 0
-#define AW_W1 16384
-#define AW_W2 32768                             // small layout, 1024
-#define AW_B(l) (AW_W2 + 1024 + (l) * 128)      // l = 0..2
-#define AW_BASIS (AW_W2 + 1024 + 3 * 128)       // thread-owned, 256 * 8
-#define AW_PART_F (AW_BASIS + 2048)
-#define AW_STASH_X (AW_PART_F)
-#define AW_STASH_H0 (AW_STASH_X + STASH_F)
-#define AW_STASH_H1 (AW_STASH_H0 + STASH_F)
-#define AW_STASH_F48 (AW_STASH_H1 + STASH_F)    // 64 x 128
-#define AW_TOTAL (AW_STASH_F48 + 64 * NVFI_TM)
-#define WS_CTA_F (VW_TOTAL > AW_TOTAL ? VW_TOTAL : AW_TOTAL)
-#define MAX_RK2_STEPS 32
-
-// ---------------------------------------------------------------------------------------
 // k_march_bwd
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

@@ -480,12 +480,15 @@ struct AdvectTile {
 
 // integrate_pos on one tile (models/tensorf_keyframe.py:575-611): RK2 midpoint steps
 // until every row's remaining offset is exactly zero.
-__device__ inline void advect_tile(const NvfiField& F, AdvectTile& T, float* actT, float* wS) {
+// `net(xs, ys, zs, ts)` evaluates the weight net on the tile and leaves the 6 basis weights in
+// T.wout (FP32 SIMT tile GEMM or the tcgen05 path of mlp_tc.cuh).
+template <class Net>
+__device__ inline void advect_tile_with(const NvfiField& F, AdvectTile& T, Net net) {
   const int tid = threadIdx.x;
   for (;;) {
     int active = (tid < NVFI_TM) ? (fabsf(T.off[tid]) > 0.f) : 0;
     if (!__syncthreads_or(active)) break;
-    vel_net_tile<ACT_SILU>(F.vel_net, actT, wS, &T.wout[0][0], T.x[0], T.x[1], T.x[2], T.tcur);
+    net(T.x[0], T.x[1], T.x[2], T.tcur);
     if (tid < NVFI_TM) {
       const int m = tid;
       const float off = T.off[m];
@@ -507,7 +510,7 @@ __device__ inline void advect_tile(const NvfiField& F, AdvectTile& T, float* act
       T.dt[m] = dt;
     }
     __syncthreads();
-    vel_net_tile<ACT_SILU>(F.vel_net, actT, wS, &T.wout[0][0], T.xm[0], T.xm[1], T.xm[2], T.tmid);
+    net(T.xm[0], T.xm[1], T.xm[2], T.tmid);
     if (tid < NVFI_TM) {
       const int m = tid;
       const float off = T.off[m];
@@ -538,6 +541,12 @@ __device__ inline void advect_tile(const NvfiField& F, AdvectTile& T, float* act
     }
     __syncthreads();
   }
+}
+
+__device__ inline void advect_tile(const NvfiField& F, AdvectTile& T, float* actT, float* wS) {
+  advect_tile_with(F, T, [&](const float* xs, const float* ys, const float* zs, const float* ts) {
+    vel_net_tile<ACT_SILU>(F.vel_net, actT, wS, &T.wout[0][0], xs, ys, zs, ts);
+  });
 }
 
 }  // namespace nvfi

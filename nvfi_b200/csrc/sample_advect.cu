@@ -14,22 +14,75 @@
 // shared-memory queue.  Whenever 128 entries are queued they are advected as one tile
 // by the FP32 tile-GEMM MLP (nvfi_common.cuh); leftovers carry over, so no tile is
 // padded except the very last one of a CTA.
+#include "mlp_tc.cuh"
 #include "nvfi_common.cuh"
 
 namespace nvfi {
 
-struct SampleQueue {
-  int q_idx[NVFI_QCAP];
-  float q_x[3][NVFI_QCAP];
-  int warp_cnt[2][NVFI_THREADS / 32];
+// ---------------------------------------------------------------------------------------
+// MLP back ends of the tile kernels.  Both evaluate the weight net of VelBasis on a tile of
+// 128 samples whose (x, y, z, t) sit in shared memory and leave the 6 basis weights in
+// outS[0..5][m]:
+//   SimtMlp  FP32 FMA tile GEMM (nvfi_common.cuh) — the verification path
+//   TcMlp    tcgen05 tensor cores, activations in TMEM (mlp_tc.cuh) — the product path
+// ---------------------------------------------------------------------------------------
+struct SimtMlp {
+  static constexpr int kThreads = NVFI_THREADS;
+  static constexpr size_t kBytes = (size_t)(NVFI_TM * NVFI_TM + 2 * NVFI_KC * 128) * sizeof(float);
+  float* actT;
+  float* wS;
+  const NvfiLinear* nets[2];
+  __device__ void init(unsigned char* p, const NvfiLinear* n0, const NvfiLinear* n1, int) {
+    actT = reinterpret_cast<float*>(p);
+    wS = actT + NVFI_TM * NVFI_TM;
+    nets[0] = n0;
+    nets[1] = n1;
+  }
+  __device__ void finish() {}
+  template <int ACT>
+  __device__ void eval(int which, float* outS, const float* xs, const float* ys, const float* zs,
+                       const float* ts) {
+    vel_net_tile<ACT>(nets[which], actT, wS, outS, xs, ys, zs, ts);
+  }
+};
+
+struct TcMlp {
+  static constexpr int kThreads = tc::kThreads;
+  static constexpr size_t kBytes = sizeof(tc::Ring) + 1024 + sizeof(tc::Ctl);
+  tc::Ring* ring;
+  tc::Ctl* ctl;
+  uint32_t dphase;
+  int mode3;
+  __device__ void init(unsigned char* p, const NvfiLinear* n0, const NvfiLinear* n1, int mode) {
+    // the swizzled operand slabs need 1024-byte alignment in the shared window
+    const uint32_t a = tc::smem_u32(p);
+    p += (1024u - (a & 1023u)) & 1023u;
+    ring = reinterpret_cast<tc::Ring*>(p);
+    ctl = reinterpret_cast<tc::Ctl*>(p + sizeof(tc::Ring));
+    dphase = 0;
+    mode3 = (mode == NVFI_MLP_TF32X3) ? 1 : 0;
+    tc::setup(*ctl, n0, n1);
+  }
+  __device__ void finish() { tc::teardown(*ctl); }
+  template <int ACT>
+  __device__ void eval(int which, float* outS, const float* xs, const float* ys, const float* zs,
+                       const float* ts) {
+    tc::vel_net_tile_tc<ACT>(*ctl, *ring, which, outS, xs, ys, zs, ts, dphase, mode3);
+  }
+};
+
+template <int NT>
+struct SampleQueue {      // capacity: a carried partial tile + one sub-batch of NT raw samples
+  int q_idx[NVFI_TM + NT];
+  float q_x[3][NVFI_TM + NT];
+  int warp_cnt[2][NT / 32];
   int batch;
 };
 
-struct SampleAdvectSmem {
-  float actT[NVFI_TM * NVFI_TM];
-  float wS[2 * NVFI_KC * 128];
+template <int NT>
+struct SampleAdvectTail {   // follows the back end's region in dynamic shared memory
   AdvectTile tile;
-  SampleQueue q;
+  SampleQueue<NT> q;
 };
 
 __device__ __forceinline__ bool eval_sample(const NvfiField& F, const NvfiRenderArgs& A,
@@ -75,11 +128,15 @@ __global__ void __launch_bounds__(256) k_sample_only(const NvfiField F, const Nv
   }
 }
 
-__global__ void __launch_bounds__(NVFI_THREADS, 2)
-    k_sample_advect(const NvfiField F, const NvfiRenderArgs A, const NvfiRenderBuffers B, int S,
-                    long long total, int n_batches) {
+template <class Mlp>
+__device__ __forceinline__ void sample_advect_body(const NvfiField& F, const NvfiRenderArgs& A,
+                                                   const NvfiRenderBuffers& B, int S,
+                                                   long long total, int n_batches, int mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SampleAdvectSmem& sm = *reinterpret_cast<SampleAdvectSmem*>(smem_raw);
+  Mlp mlp;
+  mlp.init(smem_raw, F.vel_net, nullptr, mode);
+  constexpr int NT = Mlp::kThreads;
+  SampleAdvectTail<NT>& sm = *reinterpret_cast<SampleAdvectTail<NT>*>(smem_raw + Mlp::kBytes);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   int sub = NVFI_SUBS;
@@ -102,10 +159,10 @@ __global__ void __launch_bounds__(NVFI_THREADS, 2)
           exhausted = true;
           break;
         }
-        batch_base = (long long)b * (NVFI_SUBS * NVFI_THREADS);
+        batch_base = (long long)b * (NVFI_SUBS * NT);
         sub = 0;
       }
-      const long long idx = batch_base + (long long)sub * NVFI_THREADS + tid;
+      const long long idx = batch_base + (long long)sub * NT + tid;
       ++sub;
       bool push = false;
       float xn[3] = {0.f, 0.f, 0.f};
@@ -143,7 +200,10 @@ __global__ void __launch_bounds__(NVFI_THREADS, 2)
       sm.tile.off[tid] = live ? off0 : 0.f;
     }
     __syncthreads();
-    advect_tile(F, sm.tile, sm.actT, sm.wS);
+    advect_tile_with(F, sm.tile,
+                     [&](const float* xs, const float* ys, const float* zs, const float* ts) {
+                       mlp.template eval<ACT_SILU>(0, &sm.tile.wout[0][0], xs, ys, zs, ts);
+                     });
     if (tid < n) {
       const long long gi = sm.q.q_idx[start + tid];
       B.x_adv[gi * 3 + 0] = sm.tile.x[0][tid];
@@ -152,6 +212,7 @@ __global__ void __launch_bounds__(NVFI_THREADS, 2)
     }
     __syncthreads();
   }
+  mlp.finish();
   if (B.stats) {
     float c = warp_sum((float)n_valid);
     if (lane == 0 && c > 0.f) {
@@ -159,6 +220,18 @@ __global__ void __launch_bounds__(NVFI_THREADS, 2)
       atomicAdd(reinterpret_cast<unsigned long long*>(B.stats) + 1, (unsigned long long)c);
     }
   }
+}
+
+__global__ void __launch_bounds__(NVFI_THREADS, 2)
+    k_sample_advect(const __grid_constant__ NvfiField F, const NvfiRenderArgs A,
+                    const NvfiRenderBuffers B, int S, long long total, int n_batches) {
+  sample_advect_body<SimtMlp>(F, A, B, S, total, n_batches, NVFI_MLP_FP32_SIMT);
+}
+
+__global__ void __launch_bounds__(tc::kThreads, 1)
+    k_sample_advect_tc(const __grid_constant__ NvfiField F, const NvfiRenderArgs A,
+                       const NvfiRenderBuffers B, int S, long long total, int n_batches, int mode) {
+  sample_advect_body<TcMlp>(F, A, B, S, total, n_batches, mode);
 }
 
 // Chunk-global predicate of sample_ray (models/tensorf_base.py:294): one flag per chunk
@@ -181,20 +254,21 @@ __global__ void k_chunk_inside(const NvfiField F, const float* __restrict__ rays
 // ---------------------------------------------------------------------------------------
 // Stand-alone field queries
 // ---------------------------------------------------------------------------------------
-struct PointAdvectSmem {
-  float actT[NVFI_TM * NVFI_TM];
-  float wS[2 * NVFI_KC * 128];
+struct PointAdvectTail {   // follows the back end's region in dynamic shared memory
   AdvectTile tile;
   int next;
 };
 
 // integrate_pos with per-point t / base (models/tensorf_keyframe.py:575-611).
-__global__ void __launch_bounds__(NVFI_THREADS, 2)
-    k_integrate_pos(const NvfiField F, const float* __restrict__ x, const float* __restrict__ t,
-                    const float* __restrict__ base, long long n, float* __restrict__ out,
-                    int* counter) {
+template <class Mlp>
+__device__ __forceinline__ void integrate_pos_body(const NvfiField& F, const float* __restrict__ x,
+                                                   const float* __restrict__ t,
+                                                   const float* __restrict__ base, long long n,
+                                                   float* __restrict__ out, int* counter, int mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  PointAdvectSmem& sm = *reinterpret_cast<PointAdvectSmem*>(smem_raw);
+  Mlp mlp;
+  mlp.init(smem_raw, F.vel_net, nullptr, mode);
+  PointAdvectTail& sm = *reinterpret_cast<PointAdvectTail*>(smem_raw + Mlp::kBytes);
   const int tid = threadIdx.x;
   const long long n_tiles = (n + NVFI_TM - 1) / NVFI_TM;
   for (;;) {
@@ -214,7 +288,10 @@ __global__ void __launch_bounds__(NVFI_THREADS, 2)
       sm.tile.off[tid] = live ? __fsub_rn(tt, base[i]) : 0.f;
     }
     __syncthreads();
-    advect_tile(F, sm.tile, sm.actT, sm.wS);
+    advect_tile_with(F, sm.tile,
+                     [&](const float* xs, const float* ys, const float* zs, const float* ts) {
+                       mlp.template eval<ACT_SILU>(0, &sm.tile.wout[0][0], xs, ys, zs, ts);
+                     });
     if (tid < NVFI_TM && i < n) {
       out[i * 3 + 0] = sm.tile.x[0][tid];
       out[i * 3 + 1] = sm.tile.x[1][tid];
@@ -222,14 +299,31 @@ __global__ void __launch_bounds__(NVFI_THREADS, 2)
     }
     __syncthreads();
   }
+  mlp.finish();
+}
+
+__global__ void __launch_bounds__(NVFI_THREADS, 2)
+    k_integrate_pos(const __grid_constant__ NvfiField F, const float* __restrict__ x,
+                    const float* __restrict__ t, const float* __restrict__ base, long long n,
+                    float* __restrict__ out, int* counter) {
+  integrate_pos_body<SimtMlp>(F, x, t, base, n, out, counter, NVFI_MLP_FP32_SIMT);
+}
+__global__ void __launch_bounds__(tc::kThreads, 1)
+    k_integrate_pos_tc(const __grid_constant__ NvfiField F, const float* __restrict__ x,
+                       const float* __restrict__ t, const float* __restrict__ base, long long n,
+                       float* __restrict__ out, int* counter, int mode) {
+  integrate_pos_body<TcMlp>(F, x, t, base, n, out, counter, mode);
 }
 
 // VelBasis.forward (full != 0 -> (n,6) = [v, a]) or the gated velocity (n,3).
-__global__ void __launch_bounds__(NVFI_THREADS, 2)
-    k_velocity(const NvfiField F, const float* __restrict__ xyzt, long long n, int full,
-               float* __restrict__ out, int* counter) {
+template <class Mlp>
+__device__ __forceinline__ void velocity_body(const NvfiField& F, const float* __restrict__ xyzt,
+                                              long long n, int full, float* __restrict__ out,
+                                              int* counter, int mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  PointAdvectSmem& sm = *reinterpret_cast<PointAdvectSmem*>(smem_raw);
+  Mlp mlp;
+  mlp.init(smem_raw, F.vel_net, full ? F.acc_net : nullptr, mode);
+  PointAdvectTail& sm = *reinterpret_cast<PointAdvectTail*>(smem_raw + Mlp::kBytes);
   const int tid = threadIdx.x;
   const long long n_tiles = (n + NVFI_TM - 1) / NVFI_TM;
   for (;;) {
@@ -247,8 +341,8 @@ __global__ void __launch_bounds__(NVFI_THREADS, 2)
       sm.tile.tcur[tid] = live ? xyzt[i * 4 + 3] : 0.f;
     }
     __syncthreads();
-    vel_net_tile<ACT_SILU>(F.vel_net, sm.actT, sm.wS, &sm.tile.wout[0][0], sm.tile.x[0],
-                           sm.tile.x[1], sm.tile.x[2], sm.tile.tcur);
+    mlp.template eval<ACT_SILU>(0, &sm.tile.wout[0][0], sm.tile.x[0], sm.tile.x[1], sm.tile.x[2],
+                                sm.tile.tcur);
     float v[3] = {0.f, 0.f, 0.f};
     const float px = sm.tile.x[0][tid & 127], py = sm.tile.x[1][tid & 127],
                 pz = sm.tile.x[2][tid & 127];
@@ -259,8 +353,8 @@ __global__ void __launch_bounds__(NVFI_THREADS, 2)
     }
     __syncthreads();
     if (full) {
-      vel_net_tile<ACT_RELU>(F.acc_net, sm.actT, sm.wS, &sm.tile.wout[0][0], sm.tile.x[0],
-                             sm.tile.x[1], sm.tile.x[2], sm.tile.tcur);
+      mlp.template eval<ACT_RELU>(1, &sm.tile.wout[0][0], sm.tile.x[0], sm.tile.x[1], sm.tile.x[2],
+                                  sm.tile.tcur);
       if (tid < NVFI_TM && i < n) {
         const float aw[6] = {sm.tile.wout[0][tid], sm.tile.wout[1][tid], sm.tile.wout[2][tid],
                              sm.tile.wout[3][tid], sm.tile.wout[4][tid], sm.tile.wout[5][tid]};
@@ -280,6 +374,18 @@ __global__ void __launch_bounds__(NVFI_THREADS, 2)
     }
     __syncthreads();
   }
+  mlp.finish();
+}
+
+__global__ void __launch_bounds__(NVFI_THREADS, 2)
+    k_velocity(const __grid_constant__ NvfiField F, const float* __restrict__ xyzt, long long n,
+               int full, float* __restrict__ out, int* counter) {
+  velocity_body<SimtMlp>(F, xyzt, n, full, out, counter, NVFI_MLP_FP32_SIMT);
+}
+__global__ void __launch_bounds__(tc::kThreads, 1)
+    k_velocity_tc(const __grid_constant__ NvfiField F, const float* __restrict__ xyzt, long long n,
+                  int full, float* __restrict__ out, int* counter, int mode) {
+  velocity_body<TcMlp>(F, xyzt, n, full, out, counter, mode);
 }
 
 }  // namespace nvfi
@@ -297,6 +403,24 @@ static int num_sms() {
   return g_num_sms;
 }
 
+extern "C" int nvfi_get_mlp_mode(void);
+
+// The tensor-core path needs the weight images of every layer.
+static bool has_umma(const NvfiLinear* net) {
+  for (int l = 0; l < NVFI_VEL_LAYERS; ++l)
+    if (!net[l].umma || net[l].umma_rows != (l == NVFI_VEL_LAYERS - 1 ? 16 : 128)) return false;
+  return true;
+}
+
+template <class K>
+static int set_smem(K kernel, size_t smem, size_t& cached) {
+  if (smem > cached) {
+    NVFI_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cached = smem;
+  }
+  return NVFI_OK;
+}
+
 extern "C" int nvfi_launch_sample_advect(const NvfiField* F, const NvfiRenderArgs* A,
                                          const NvfiRenderBuffers* B, cudaStream_t st) {
   const int S = F->n_samples;
@@ -312,14 +436,24 @@ extern "C" int nvfi_launch_sample_advect(const NvfiField* F, const NvfiRenderArg
     NVFI_LAUNCH(k_sample_only, grid, 256, 0, st, *F, *A, *B, S, total);
     return (int)cudaGetLastError();
   }
-  const size_t smem = sizeof(SampleAdvectSmem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NVFI_CUDA_OK(cudaFuncSetAttribute(k_sample_advect, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-    attr_set = true;
+  const int mode = nvfi_get_mlp_mode();
+  if (mode != NVFI_MLP_FP32_SIMT) {
+    if (!has_umma(F->vel_net)) return NVFI_EINVAL;
+    const int per_batch = NVFI_SUBS * TcMlp::kThreads;
+    const int n_batches = (int)((total + per_batch - 1) / per_batch);
+    const size_t smem = TcMlp::kBytes + sizeof(SampleAdvectTail<TcMlp::kThreads>);
+    static size_t cached = 0;
+    int rc = set_smem(k_sample_advect_tc, smem, cached);
+    if (rc != NVFI_OK) return rc;
+    const int grid = min(n_batches, num_sms());
+    NVFI_LAUNCH(k_sample_advect_tc, grid, TcMlp::kThreads, smem, st, *F, *A, *B, S, total, n_batches, mode);
+    return (int)cudaGetLastError();
   }
   const int n_batches = (int)((total + NVFI_SUBS * NVFI_THREADS - 1) / (NVFI_SUBS * NVFI_THREADS));
+  const size_t smem = SimtMlp::kBytes + sizeof(SampleAdvectTail<NVFI_THREADS>);
+  static size_t cached = 0;
+  int rc = set_smem(k_sample_advect, smem, cached);
+  if (rc != NVFI_OK) return rc;
   const int grid = min(n_batches, num_sms() * 2);
   NVFI_LAUNCH(k_sample_advect, grid, NVFI_THREADS, smem, st, *F, *A, *B, S, total, n_batches);
   return (int)cudaGetLastError();
@@ -331,15 +465,23 @@ extern "C" int nvfi_integrate_pos(const NvfiField* F, const float* x, const floa
   if (!F || !x || !t || !base || !out || !counters || n < 0) return NVFI_EINVAL;
   if (n == 0) return NVFI_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = sizeof(PointAdvectSmem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NVFI_CUDA_OK(cudaFuncSetAttribute(k_integrate_pos, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-    attr_set = true;
-  }
   NVFI_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(int32_t), st));
   const long long n_tiles = (n + NVFI_TM - 1) / NVFI_TM;
+  const int mode = nvfi_get_mlp_mode();
+  if (mode != NVFI_MLP_FP32_SIMT) {
+    if (!has_umma(F->vel_net)) return NVFI_EINVAL;
+    const size_t smem = TcMlp::kBytes + sizeof(PointAdvectTail);
+    static size_t cached = 0;
+    int rc = set_smem(k_integrate_pos_tc, smem, cached);
+    if (rc != NVFI_OK) return rc;
+    const int grid = (int)(n_tiles < (long long)num_sms() ? n_tiles : (long long)num_sms());
+    NVFI_LAUNCH(k_integrate_pos_tc, grid, TcMlp::kThreads, smem, st, *F, x, t, base, n, out, counters, mode);
+    return (int)cudaGetLastError();
+  }
+  const size_t smem = SimtMlp::kBytes + sizeof(PointAdvectTail);
+  static size_t cached = 0;
+  int rc = set_smem(k_integrate_pos, smem, cached);
+  if (rc != NVFI_OK) return rc;
   const int grid = (int)(n_tiles < (long long)num_sms() * 2 ? n_tiles : (long long)num_sms() * 2);
   NVFI_LAUNCH(k_integrate_pos, grid, NVFI_THREADS, smem, st, *F, x, t, base, n, out, counters);
   return (int)cudaGetLastError();
@@ -350,15 +492,23 @@ extern "C" int nvfi_velocity(const NvfiField* F, const float* xyzt, int64_t n, i
   if (!F || !xyzt || !out || !counters || n < 0) return NVFI_EINVAL;
   if (n == 0) return NVFI_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = sizeof(PointAdvectSmem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NVFI_CUDA_OK(cudaFuncSetAttribute(k_velocity, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-    attr_set = true;
-  }
   NVFI_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(int32_t), st));
   const long long n_tiles = (n + NVFI_TM - 1) / NVFI_TM;
+  const int mode = nvfi_get_mlp_mode();
+  if (mode != NVFI_MLP_FP32_SIMT) {
+    if (!has_umma(F->vel_net) || (full && !has_umma(F->acc_net))) return NVFI_EINVAL;
+    const size_t smem = TcMlp::kBytes + sizeof(PointAdvectTail);
+    static size_t cached = 0;
+    int rc = set_smem(k_velocity_tc, smem, cached);
+    if (rc != NVFI_OK) return rc;
+    const int grid = (int)(n_tiles < (long long)num_sms() ? n_tiles : (long long)num_sms());
+    NVFI_LAUNCH(k_velocity_tc, grid, TcMlp::kThreads, smem, st, *F, xyzt, n, full, out, counters, mode);
+    return (int)cudaGetLastError();
+  }
+  const size_t smem = SimtMlp::kBytes + sizeof(PointAdvectTail);
+  static size_t cached = 0;
+  int rc = set_smem(k_velocity, smem, cached);
+  if (rc != NVFI_OK) return rc;
   const int grid = (int)(n_tiles < (long long)num_sms() * 2 ? n_tiles : (long long)num_sms() * 2);
   NVFI_LAUNCH(k_velocity, grid, NVFI_THREADS, smem, st, *F, xyzt, n, full, out, counters);
   return (int)cudaGetLastError();

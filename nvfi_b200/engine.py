@@ -26,6 +26,19 @@ MAT_MODE_SPACE = ((0, 1), (0, 2), (1, 2))
 MAT_MODE_TIME = ((2, 3), (1, 3), (0, 3))
 
 
+MLP_MODES = {"simt": L.MLP_FP32_SIMT, "tf32x3": L.MLP_TF32X3, "tf32": L.MLP_TF32}
+
+
+def set_mlp_mode(mode: str) -> str:
+    """Arithmetic of the velocity-MLP GEMMs: 'tf32x3' (tcgen05 tensor cores, FP32-grade 3-term
+    split; default), 'tf32' (single pass, fastest) or 'simt' (FP32 FMA verification path).
+    Returns the previous mode."""
+    prev = L.load().nvfi_set_mlp_mode(MLP_MODES[mode])
+    if prev < 0:
+        raise RuntimeError("nvfi_b200: bad mlp mode")
+    return {v: k for k, v in MLP_MODES.items()}[prev]
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -62,7 +75,7 @@ class PackedLinear:
     """nn.Linear weight (out,in)[, bias] -> zero-padded W^T (k_pad, n_pad) [+ (n_pad)]."""
 
     def __init__(self, out_dim: int, in_dim: int, device, hidden: bool, has_bias: bool = True,
-                 diff: bool = False):
+                 diff: bool = False, umma: bool = False):
         self.out_dim, self.in_dim = out_dim, in_dim
         self.k_pad = _round_up(in_dim, 32)
         self.n_pad = 128 if hidden else _round_up(out_dim, 4)
@@ -73,6 +86,10 @@ class PackedLinear:
         # W zero-padded to (128, k_pad) for the input-gradient GEMM of the backward pass
         self.w_rows = (torch.zeros(128, self.k_pad, device=device, dtype=torch.float32)
                        if (hidden and diff) else None)
+        # tensor-core image (hi/lo TF32 slabs per 32-wide K block, 128B-swizzled K-major)
+        self.umma_rows = (128 if hidden else _round_up(out_dim, 16)) if umma else 0
+        self.umma = (torch.zeros((self.k_pad // 32) * 2 * self.umma_rows * 32, device=device,
+                                 dtype=torch.float32) if umma else None)
         self.track = _Tracked()
 
     def sync(self, w: torch.Tensor, b: Optional[torch.Tensor]):
@@ -86,11 +103,16 @@ class PackedLinear:
                 "pack_linear")
         if self.w_rows is not None:
             self.w_rows[:self.out_dim, :self.in_dim].copy_(wd)
+        if self.umma is not None:
+            L.check(lib.nvfi_pack_linear_umma(wd.data_ptr(), self.umma.data_ptr(), self.out_dim, self.in_dim,
+                                              self.umma_rows, self.k_pad, _stream()), "pack_linear_umma")
 
     def fill(self, s: L.NvfiLinear):
         s.wt = self.wt.data_ptr()
         s.bias = _ptr(self.bias)
         s.w_rows = _ptr(self.w_rows)
+        s.umma = _ptr(self.umma)
+        s.umma_rows = self.umma_rows
         s.in_dim, s.out_dim, s.k_pad, s.n_pad = self.in_dim, self.out_dim, self.k_pad, self.n_pad
 
     def unpack_grad(self, g_wt: torch.Tensor, g_b: Optional[torch.Tensor], want_bias: bool):
@@ -227,8 +249,9 @@ class FieldBinding:
         if f.use_vel:
             if self.vel is None:
                 dims = [(128, 28)] + [(128, 128)] * 4 + [(6, 128)]
-                self.vel = [PackedLinear(o, i, dev, hidden=(j < 5), diff=True) for j, (o, i) in enumerate(dims)]
-                self.acc = [PackedLinear(o, i, dev, hidden=(j < 5)) for j, (o, i) in enumerate(dims)]
+                self.vel = [PackedLinear(o, i, dev, hidden=(j < 5), diff=True, umma=True)
+                            for j, (o, i) in enumerate(dims)]
+                self.acc = [PackedLinear(o, i, dev, hidden=(j < 5), umma=True) for j, (o, i) in enumerate(dims)]
             for j, (w, b) in enumerate(vel_linears(f.vel_net.weight_net)):
                 self.vel[j].sync(w, b)
                 self.vel[j].fill(s.vel_net[j])
@@ -473,6 +496,8 @@ def integrate_pos(binding: FieldBinding, x: torch.Tensor, t: torch.Tensor, base:
     t = t.detach().reshape(-1).contiguous().float()
     base = base.detach().reshape(-1).contiguous().float()
     out = torch.empty_like(x)
+    if n == 0:
+        return out
     cnt = _counters(x.device)
     L.check(L.load().nvfi_integrate_pos(C.byref(s), x.data_ptr(), t.data_ptr(), base.data_ptr(), n,
                                         out.data_ptr(), cnt.data_ptr(), _stream()), "integrate_pos")
@@ -484,6 +509,8 @@ def density_feature(binding: FieldBinding, xyzt: torch.Tensor) -> torch.Tensor:
     xyzt = xyzt.detach().reshape(-1, 4).contiguous().float()
     n = xyzt.shape[0]
     out = torch.empty(n, 1, device=xyzt.device, dtype=torch.float32)
+    if n == 0:
+        return out
     L.check(L.load().nvfi_density_feature(C.byref(s), xyzt.data_ptr(), n, out.data_ptr(), _stream()),
             "density_feature")
     return out
@@ -494,6 +521,8 @@ def density_sigma(binding: FieldBinding, xyzt: torch.Tensor) -> torch.Tensor:
     xyzt = xyzt.detach().reshape(-1, 4).contiguous().float()
     n = xyzt.shape[0]
     out = torch.empty(n, device=xyzt.device, dtype=torch.float32)
+    if n == 0:
+        return out
     L.check(L.load().nvfi_density_sigma(C.byref(s), xyzt.data_ptr(), n, out.data_ptr(), _stream()),
             "density_sigma")
     return out
@@ -503,6 +532,8 @@ def feature2density(binding: FieldBinding, feat: torch.Tensor) -> torch.Tensor:
     s = binding.sync()
     f = feat.detach().contiguous().float()
     out = torch.empty_like(f)
+    if f.numel() == 0:
+        return out
     L.check(L.load().nvfi_feature2density(C.byref(s), f.data_ptr(), f.numel(), out.data_ptr(), _stream()),
             "feature2density")
     return out
@@ -513,6 +544,8 @@ def app_feature(binding: FieldBinding, xyzt: torch.Tensor) -> torch.Tensor:
     xyzt = xyzt.detach().reshape(-1, 4).contiguous().float()
     n = xyzt.shape[0]
     out = torch.empty(n, int(s.app_dim), device=xyzt.device, dtype=torch.float32)
+    if n == 0:
+        return out
     cnt = _counters(xyzt.device)
     L.check(L.load().nvfi_app_feature(C.byref(s), xyzt.data_ptr(), n, out.data_ptr(), cnt.data_ptr(),
                                       _stream()), "app_feature")
@@ -524,6 +557,8 @@ def velocity(binding: FieldBinding, xyzt: torch.Tensor, full: bool) -> torch.Ten
     xyzt = xyzt.detach().reshape(-1, 4).contiguous().float()
     n = xyzt.shape[0]
     out = torch.empty(n, 6 if full else 3, device=xyzt.device, dtype=torch.float32)
+    if n == 0:
+        return out
     cnt = _counters(xyzt.device)
     L.check(L.load().nvfi_velocity(C.byref(s), xyzt.data_ptr(), n, 1 if full else 0, out.data_ptr(),
                                    cnt.data_ptr(), _stream()), "velocity")

@@ -1,0 +1,96 @@
+"""GPU parity of the PDE loss (NVFi.get_vel_loss, models/nvfi.py:42-84): loss value and the
+gradients w.r.t. both weight nets against the reference's own output (golden fixtures, made
+with functorch vmap(jacrev) + autograd) and against the CPU oracle on larger random inputs.
+Tolerance 1e-4 relative (loss) / 1e-4 relative norm (gradients)."""
+import pytest
+import torch
+
+from oracle import nvfi_oracle as O
+from tests.helpers import GOLDEN_SCENES, Golden, build_model, norm_rel_err, oracle_param_map
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module", params=GOLDEN_SCENES)
+def g(request):
+    return Golden(request.param)
+
+
+def _points(g, sc):
+    pu, t = g.t("pde/points_u"), g.t("pde/t")
+    pts = pu * (sc.aabb[1] - sc.aabb[0]) + sc.aabb[0]
+    return O.normalize_coord(sc, pts), t
+
+
+def test_vel_loss_vs_reference(g):
+    sc = g.scene()
+    pn, t = _points(g, sc)
+    model = build_model(g, requires_grad=True)
+    loss = model.get_vel_loss(pn.shape[0], points=pn.cuda(), t=t.cuda())
+    if bool(g.z["pde/empty"]):
+        assert loss == 0.0
+        return
+    ref = float(g.z["pde/loss"])
+    assert abs(loss.item() - ref) < TOL * max(1.0, abs(ref))
+    loss.backward()
+    params = dict(model.nvfi.named_parameters())
+    n = 0
+    for k in g.keys("pde/grad/"):
+        name = k[len("pde/grad/"):]
+        assert params[name].grad is not None, name
+        assert norm_rel_err(params[name].grad.cpu(), g.z[k]) < TOL, name
+        n += 1
+    assert n == 24
+    # nothing else receives a gradient from the PDE loss
+    for name, p in params.items():
+        if "vel_net" not in name:
+            assert p.grad is None, name
+
+
+def test_occupancy_filter_matches_oracle(g):
+    from nvfi_b200 import pde
+    sc = g.scene()
+    pn, t = _points(g, sc)
+    model = build_model(g)
+    keep = pde.occupancy_filter(model.nvfi, pn.cuda(), t.cuda()).cpu()
+    ref = O.occupancy_filter(sc, pn, t)
+    # membership may only differ where alpha sits within rounding of the threshold
+    assert int((keep != ref).sum()) <= max(1, int(0.001 * ref.numel()))
+
+
+def test_pde_on_dense_points_vs_oracle(g):
+    """No occupancy filter: every point contributes (ragged tile tails: 25 points per tile)."""
+    from nvfi_b200 import pde
+    gen = torch.Generator().manual_seed(11)
+    for n in (1, 24, 26, 777):
+        xyzt = torch.cat([torch.rand(n, 3, generator=gen) * 1.8 - 0.9, torch.rand(n, 1, generator=gen)], -1)
+        sc = g.scene(requires_grad=True)
+        ref = O.pde_loss_from_points(sc, xyzt)
+        ref.backward()
+        model = build_model(g, requires_grad=True)
+        loss = pde.pde_loss_from_points(model.nvfi, xyzt.cuda())
+        assert abs(loss.item() - ref.item()) < TOL * max(1.0, abs(ref.item())), n
+        (2.5 * loss).backward()     # upstream scale is applied
+        pm = oracle_param_map(sc)
+        params = dict(model.nvfi.named_parameters())
+        for name, p in pm.items():
+            if "vel_net" in name and p.grad is not None:
+                assert norm_rel_err(params[name].grad.cpu(), 2.5 * p.grad) < TOL, (n, name)
+
+
+def test_no_grad_mode_and_accumulation(g):
+    from nvfi_b200 import pde
+    gen = torch.Generator().manual_seed(3)
+    xyzt = torch.cat([torch.rand(300, 3, generator=gen) * 1.6 - 0.8, torch.rand(300, 1, generator=gen)], -1).cuda()
+    model = build_model(g, requires_grad=True)
+    with torch.no_grad():
+        l0 = pde.pde_loss_from_points(model.nvfi, xyzt)
+    assert not l0.requires_grad
+    l1 = pde.pde_loss_from_points(model.nvfi, xyzt)
+    assert abs(l0.item() - l1.item()) < 1e-6 * max(1.0, abs(l1.item()))
+    l1.backward()
+    p = dict(model.nvfi.named_parameters())["vel_net.weight_net.4.0.weight"]
+    g1 = p.grad.clone()
+    pde.pde_loss_from_points(model.nvfi, xyzt).backward()     # grads accumulate like autograd
+    assert norm_rel_err(p.grad, 2 * g1) < 1e-5

@@ -65,6 +65,15 @@ out = f.render_rays(float(case["t"]), o.cuda(), d.cuda(), white_bg=white, ray_ch
                     jitter=torch.from_numpy(case["jitter"]), chunk_bg=bg)
 lwc = {k: (v.cuda() if k in keys else torch.zeros_like(v).cuda()) for k, v in lw.items()}
 scalar_loss(out, lwc).backward()
+run1 = {k: v.grad.detach().clone() for k, v in f.named_parameters() if v.grad is not None}
+# run-to-run noise of the atomics-based accumulation: same inputs, second backward
+model.zero_grad(set_to_none=True)
+out2 = f.render_rays(float(case["t"]), o.cuda(), d.cuda(), white_bg=white, ray_chunk=g.ray_chunk,
+                     jitter=torch.from_numpy(case["jitter"]), chunk_bg=bg)
+scalar_loss(out2, lwc).backward()
+for k, v in f.named_parameters():
+    if v.grad is not None and k in run1 and ("density_plane" in k or "weight_net.1.weight" in k):
+        print(f"run-to-run {k:32s} {norm_rel_err(v.grad.cpu(), run1[k].cpu()):.2e}")
 dbg = engine.DEBUG_KEEP
 fo = engine.DEBUG_KEEP["fwd"]
 x64, x32 = FWD["torch.float64"]["x"], FWD["torch.float32"]["x"]
@@ -89,3 +98,28 @@ k = "density_plane_time.1"
 e = (params[k].grad.cpu().double() - g64[k]).abs()
 idx = torch.topk(e.reshape(-1), 5).indices
 print("worst entries of", k, [(int(i), float(e.reshape(-1)[i]), float(g64[k].reshape(-1)[i])) for i in idx])
+
+# ---- does the density-plane error come from the scatter or from dL/dsigma?  Push MY dL/dsigma and
+# the oracle32's through an exact (float64) density backward and compare with the f64 gradient.
+torch.set_default_dtype(torch.float64)
+sc64 = g.scene()
+for fld in dataclasses.fields(sc64):
+    v_ = getattr(sc64, fld.name)
+    if torch.is_tensor(v_): setattr(sc64, fld.name, v_.double())
+    elif isinstance(v_, list) and v_ and torch.is_tensor(v_[0]): setattr(sc64, fld.name, [x.double().requires_grad_(True) for x in v_])
+    elif isinstance(v_, list) and v_ and isinstance(v_[0], tuple): setattr(sc64, fld.name, [(w.double(), b.double()) for w, b in v_])
+tt = torch.full((1, 1), float(case["t"]))
+base = O.keyframe_snap(sc64, tt)
+tnb = float(O.normalize_time_coord(sc64, base))
+vmask = valid
+xv = x64[vmask]
+xyzt = torch.cat([xv, torch.full((xv.shape[0], 1), tnb)], -1)
+sig = O.feature2density(sc64, O.density_feature(sc64, xyzt))
+planes = list(sc64.density_plane_space) + list(sc64.density_plane_time)
+names = [f"density_plane_space.{k}" for k in range(3)] + [f"density_plane_time.{k}" for k in range(3)]
+for label, gsv in (("mine", gs), ("oracle32", gs32), ("f64", gs64)):
+    grads = torch.autograd.grad(sig, planes, grad_outputs=gsv[vmask].double(), retain_graph=True)
+    print("exact density backward of dL/dsigma from", label, {n[14:]: f"{norm_rel_err(gr, g64[n]):.2e}" for n, gr in zip(names, grads)})
+    if label == "mine":
+        print("   vs MY plane grads      ", {n[14:]: f"{norm_rel_err(params[n].grad.cpu().double(), gr):.2e}" for n, gr in zip(names, grads)})
+torch.set_default_dtype(torch.float32)
