@@ -51,6 +51,7 @@ struct TcMlp {
   static constexpr size_t kBytes = sizeof(tc::Ring) + 1024 + sizeof(tc::Ctl);
   tc::Ring* ring;
   tc::Ctl* ctl;
+  tc::Issuer is;
   uint32_t dphase;
   int mode3;
   __device__ void init(unsigned char* p, const NvfiLinear* n0, const NvfiLinear* n1, int mode) {
@@ -62,12 +63,13 @@ struct TcMlp {
     dphase = 0;
     mode3 = (mode == NVFI_MLP_TF32X3) ? 1 : 0;
     tc::setup(*ctl, n0, n1);
+    is.init(*ctl, *ring);
   }
-  __device__ void finish() { tc::teardown(*ctl); }
+  __device__ void finish() { tc::teardown(*ctl, is); }
   template <int ACT>
   __device__ void eval(int which, float* outS, const float* xs, const float* ys, const float* zs,
                        const float* ts) {
-    tc::vel_net_tile_tc<ACT>(*ctl, *ring, which, outS, xs, ys, zs, ts, dphase, mode3);
+    tc::vel_net_tile_tc<ACT>(*ctl, is, which, outS, xs, ys, zs, ts, dphase, mode3);
   }
 };
 

@@ -251,7 +251,8 @@ class FieldBinding:
                 dims = [(128, 28)] + [(128, 128)] * 4 + [(6, 128)]
                 self.vel = [PackedLinear(o, i, dev, hidden=(j < 5), diff=True, umma=True)
                             for j, (o, i) in enumerate(dims)]
-                self.acc = [PackedLinear(o, i, dev, hidden=(j < 5), umma=True) for j, (o, i) in enumerate(dims)]
+                self.acc = [PackedLinear(o, i, dev, hidden=(j < 5), diff=True, umma=True)
+                            for j, (o, i) in enumerate(dims)]
             for j, (w, b) in enumerate(vel_linears(f.vel_net.weight_net)):
                 self.vel[j].sync(w, b)
                 self.vel[j].fill(s.vel_net[j])

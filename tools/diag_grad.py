@@ -37,7 +37,7 @@ def run_oracle(dtype):
         r = O.render_chunk(sc, float(case["t"]), o[sl].to(dtype), d[sl].to(dtype), white_bg=white, training=True,
                            jitter=torch.from_numpy(case["jitter"])[sl].to(dtype), random_bg=bool(rb[c]) if rb else False,
                            return_aux=True)
-        aux = r[5]; aux["sigma"].retain_grad(); aux["xyz_adv"].retain_grad() if (aux["xyz_adv"].requires_grad and not aux["xyz_adv"].is_leaf) else None
+        aux = r[5]; aux["sigma"].retain_grad(); aux["rgb"].retain_grad() if aux["rgb"].requires_grad else None; aux["xyz_adv"].retain_grad() if (aux["xyz_adv"].requires_grad and not aux["xyz_adv"].is_leaf) else None
         auxs.append(aux)
         l = 0
         for key, idx in (("wr", 0), ("wd", 1), ("wa", 2), ("ww", 3)):
@@ -50,7 +50,7 @@ def run_oracle(dtype):
     gx = torch.cat([a["xyz_adv"].grad if (a["xyz_adv"].requires_grad and a["xyz_adv"].grad is not None) else torch.zeros_like(a["xyz_adv"]) for a in auxs], 0)
     valid = torch.cat([a["valid"] for a in auxs], 0)
     torch.set_default_dtype(torch.float32)
-    FWD[str(dtype)] = dict(x=torch.cat([a["xyz_adv"].detach() for a in auxs], 0).double(),
+    FWD[str(dtype)] = dict(rgb=torch.cat([a["rgb"].detach() for a in auxs], 0).double(), x=torch.cat([a["xyz_adv"].detach() for a in auxs], 0).double(),
                            sigma=torch.cat([a["sigma"].detach() for a in auxs], 0).double())
     return {k: v.grad.double() for k, v in pm.items() if v.grad is not None}, gs.double(), gx.double(), valid
 
@@ -123,3 +123,34 @@ for label, gsv in (("mine", gs), ("oracle32", gs32), ("f64", gs64)):
     if label == "mine":
         print("   vs MY plane grads      ", {n[14:]: f"{norm_rel_err(params[n].grad.cpu().double(), gr):.2e}" for n, gr in zip(names, grads)})
 torch.set_default_dtype(torch.float32)
+
+# ---- structure of the dL/dsigma error: by sample class and per-ray correlation
+dm, do = (gs - gs64), (gs32 - gs64)
+N, S = gs64.shape
+first_app = torch.full((N,), S, dtype=torch.long)
+thr = 1e-4
+wm = fo.weights.cpu().double()
+is_app = wm > thr
+idx = torch.arange(S)[None, :].expand(N, S)
+first_app = torch.where(is_app, idx, torch.full_like(idx, S)).amin(1)
+before = (idx < first_app[:, None]) & valid
+after = (idx > first_app[:, None]) & valid & ~is_app
+for name, msk in (("before first app sample", before), ("app samples", is_app & valid), ("behind, non-app", after)):
+    if msk.any():
+        nr = gs64[msk].norm()
+        print(f"{name:26s} n={int(msk.sum()):7d} |g|={float(nr):.3e}  mine {float(dm[msk].norm()/nr):.2e}  o32 {float(do[msk].norm()/nr):.2e}"
+              f"   slope mine {float((dm[msk]*gs64[msk]).sum()/(nr*nr)):+.2e}  o32 {float((do[msk]*gs64[msk]).sum()/(nr*nr)):+.2e}")
+# per-ray relative scale error of the 'before' samples (R_i is shared by them)
+num_m = (dm * gs64 * before).sum(1); num_o = (do * gs64 * before).sum(1); den = (gs64 * gs64 * before).sum(1)
+ok = den > 0
+rm, ro = (num_m[ok] / den[ok]), (num_o[ok] / den[ok])
+print("per-ray scale error of dL/dsigma (before-surface samples): mine rms %.2e max %.2e ; o32 rms %.2e max %.2e" % (
+    float(rm.pow(2).mean().sqrt()), float(rm.abs().max()), float(ro.pow(2).mean().sqrt()), float(ro.abs().max())))
+# forward colour / weight agreement
+rgb_m = fo.rgb.cpu().double()
+
+r64, r32 = FWD["torch.float64"]["rgb"], FWD["torch.float32"]["rgb"]
+am = is_app & valid
+print("per-sample rgb (app samples): mine-vs-f64 max %.2e rms %.2e ; o32-vs-f64 max %.2e rms %.2e" % (
+    float((rgb_m[am] - r64[am]).abs().max()), float((rgb_m[am] - r64[am]).pow(2).mean().sqrt()),
+    float((r32[am] - r64[am]).abs().max()), float((r32[am] - r64[am]).pow(2).mean().sqrt())))
