@@ -52,7 +52,7 @@ struct TcMlp {
   tc::Ring* ring;
   tc::Ctl* ctl;
   tc::Issuer is;
-  uint32_t dphase;
+  uint32_t dphase, kphase;
   int mode3;
   __device__ void init(unsigned char* p, const NvfiLinear* n0, const NvfiLinear* n1, int mode) {
     // the swizzled operand slabs need 1024-byte alignment in the shared window
@@ -61,6 +61,7 @@ struct TcMlp {
     ring = reinterpret_cast<tc::Ring*>(p);
     ctl = reinterpret_cast<tc::Ctl*>(p + sizeof(tc::Ring));
     dphase = 0;
+    kphase = 0;
     mode3 = (mode == NVFI_MLP_TF32X3) ? 1 : 0;
     tc::setup(*ctl, n0, n1);
     is.init(*ctl, *ring);
@@ -69,7 +70,7 @@ struct TcMlp {
   template <int ACT>
   __device__ void eval(int which, float* outS, const float* xs, const float* ys, const float* zs,
                        const float* ts) {
-    tc::vel_net_tile_tc<ACT>(*ctl, is, which, outS, xs, ys, zs, ts, dphase, mode3);
+    tc::vel_net_tile_tc<ACT>(*ctl, is, which, outS, xs, ys, zs, ts, dphase, kphase, mode3);
   }
 };
 

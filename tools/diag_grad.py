@@ -144,7 +144,7 @@ for name, msk in (("before first app sample", before), ("app samples", is_app & 
 num_m = (dm * gs64 * before).sum(1); num_o = (do * gs64 * before).sum(1); den = (gs64 * gs64 * before).sum(1)
 ok = den > 0
 rm, ro = (num_m[ok] / den[ok]), (num_o[ok] / den[ok])
-print("per-ray scale error of dL/dsigma (before-surface samples): mine rms %.2e max %.2e ; o32 rms %.2e max %.2e" % (
+if int(ok.sum()) > 0: print("per-ray scale error of dL/dsigma (before-surface samples): mine rms %.2e max %.2e ; o32 rms %.2e max %.2e" % (
     float(rm.pow(2).mean().sqrt()), float(rm.abs().max()), float(ro.pow(2).mean().sqrt()), float(ro.abs().max())))
 # forward colour / weight agreement
 rgb_m = fo.rgb.cpu().double()
