@@ -27,7 +27,8 @@ namespace nvfi {
 //   TcMlp    tcgen05 tensor cores, activations in TMEM (mlp_tc.cuh) — the product path
 // ---------------------------------------------------------------------------------------
 struct SimtMlp {
-  static constexpr int kThreads = NVFI_THREADS;
+  static constexpr int kThreads = NVFI_THREADS;        // threads that take part in the tile work
+  static constexpr int kLaunchThreads = NVFI_THREADS;  // threads per CTA
   static constexpr size_t kBytes = (size_t)(NVFI_TM * NVFI_TM + 2 * NVFI_KC * 128) * sizeof(float);
   float* actT;
   float* wS;
@@ -48,6 +49,7 @@ struct SimtMlp {
 
 struct TcMlp {
   static constexpr int kThreads = tc::kThreads;
+  static constexpr int kLaunchThreads = tc::kLaunchThreads;   // + the issuer warp
   static constexpr size_t kBytes = sizeof(tc::Ring) + 1024 + sizeof(tc::Ctl);
   tc::Ring* ring;
   tc::Ctl* ctl;
@@ -169,12 +171,12 @@ __device__ __forceinline__ void sample_advect_body(const NvfiField& F, const Nvf
       ++sub;
       bool push = false;
       float xn[3] = {0.f, 0.f, 0.f};
-      if (idx < total) {
+      if (tid < NT && idx < total) {     // (a back end may run extra warps that only join barriers)
         push = eval_sample(F, A, B, idx, S, xn);
         B.valid[idx] = push ? 1 : 0;
       }
       const unsigned bal = __ballot_sync(0xffffffffu, push);
-      if (lane == 0) sm.q.warp_cnt[par][warp] = __popc(bal);
+      if (lane == 0 && warp < NT / 32) sm.q.warp_cnt[par][warp] = __popc(bal);
       const int tot = __syncthreads_count(push);
       if (push) {
         int pos = qc + __popc(bal & ((1u << lane) - 1u));
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(NVFI_THREADS, 2)
   sample_advect_body<SimtMlp>(F, A, B, S, total, n_batches, NVFI_MLP_FP32_SIMT);
 }
 
-__global__ void __launch_bounds__(tc::kThreads, 1)
+__global__ void __launch_bounds__(tc::kLaunchThreads, 1)
     k_sample_advect_tc(const __grid_constant__ NvfiField F, const NvfiRenderArgs A,
                        const NvfiRenderBuffers B, int S, long long total, int n_batches, int mode) {
   sample_advect_body<TcMlp>(F, A, B, S, total, n_batches, mode);
@@ -311,7 +313,7 @@ __global__ void __launch_bounds__(NVFI_THREADS, 2)
                     float* __restrict__ out, int* counter) {
   integrate_pos_body<SimtMlp>(F, x, t, base, n, out, counter, NVFI_MLP_FP32_SIMT);
 }
-__global__ void __launch_bounds__(tc::kThreads, 1)
+__global__ void __launch_bounds__(tc::kLaunchThreads, 1)
     k_integrate_pos_tc(const __grid_constant__ NvfiField F, const float* __restrict__ x,
                        const float* __restrict__ t, const float* __restrict__ base, long long n,
                        float* __restrict__ out, int* counter, int mode) {
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(NVFI_THREADS, 2)
                int full, float* __restrict__ out, int* counter) {
   velocity_body<SimtMlp>(F, xyzt, n, full, out, counter, NVFI_MLP_FP32_SIMT);
 }
-__global__ void __launch_bounds__(tc::kThreads, 1)
+__global__ void __launch_bounds__(tc::kLaunchThreads, 1)
     k_velocity_tc(const __grid_constant__ NvfiField F, const float* __restrict__ xyzt, long long n,
                   int full, float* __restrict__ out, int* counter, int mode) {
   velocity_body<TcMlp>(F, xyzt, n, full, out, counter, mode);
@@ -449,7 +451,7 @@ extern "C" int nvfi_launch_sample_advect(const NvfiField* F, const NvfiRenderArg
     int rc = set_smem(k_sample_advect_tc, smem, cached);
     if (rc != NVFI_OK) return rc;
     const int grid = min(n_batches, num_sms());
-    NVFI_LAUNCH(k_sample_advect_tc, grid, TcMlp::kThreads, smem, st, *F, *A, *B, S, total, n_batches, mode);
+    NVFI_LAUNCH(k_sample_advect_tc, grid, TcMlp::kLaunchThreads, smem, st, *F, *A, *B, S, total, n_batches, mode);
     return (int)cudaGetLastError();
   }
   const int n_batches = (int)((total + NVFI_SUBS * NVFI_THREADS - 1) / (NVFI_SUBS * NVFI_THREADS));
@@ -478,7 +480,7 @@ extern "C" int nvfi_integrate_pos(const NvfiField* F, const float* x, const floa
     int rc = set_smem(k_integrate_pos_tc, smem, cached);
     if (rc != NVFI_OK) return rc;
     const int grid = (int)(n_tiles < (long long)num_sms() ? n_tiles : (long long)num_sms());
-    NVFI_LAUNCH(k_integrate_pos_tc, grid, TcMlp::kThreads, smem, st, *F, x, t, base, n, out, counters, mode);
+    NVFI_LAUNCH(k_integrate_pos_tc, grid, TcMlp::kLaunchThreads, smem, st, *F, x, t, base, n, out, counters, mode);
     return (int)cudaGetLastError();
   }
   const size_t smem = SimtMlp::kBytes + sizeof(PointAdvectTail);
@@ -505,7 +507,7 @@ extern "C" int nvfi_velocity(const NvfiField* F, const float* xyzt, int64_t n, i
     int rc = set_smem(k_velocity_tc, smem, cached);
     if (rc != NVFI_OK) return rc;
     const int grid = (int)(n_tiles < (long long)num_sms() ? n_tiles : (long long)num_sms());
-    NVFI_LAUNCH(k_velocity_tc, grid, TcMlp::kThreads, smem, st, *F, xyzt, n, full, out, counters, mode);
+    NVFI_LAUNCH(k_velocity_tc, grid, TcMlp::kLaunchThreads, smem, st, *F, xyzt, n, full, out, counters, mode);
     return (int)cudaGetLastError();
   }
   const size_t smem = SimtMlp::kBytes + sizeof(PointAdvectTail);
