@@ -332,7 +332,9 @@ def run_gpu(args):
         S = 192
         alg = {   # kernel -> (bound, algorithmic work per launch)
             "k_sample_advect": ("tensor", n_adv * 2 * VEL_EVAL_FLOP),
+            "k_sample_advect_tc": ("tensor", n_adv * 2 * VEL_EVAL_FLOP),
             "k_advect_bwd": ("tensor", n_adv_bwd * 6 * VEL_EVAL_FLOP),   # 2 evals: fwd recompute + dX + dW GEMMs
+            "k_advect_bwd_tc": ("tensor", n_adv_bwd * 6 * VEL_EVAL_FLOP),
             "k_march": ("hbm", n_valid * DENSITY_BYTES + n * (44 + 4 * S)),
             "k_density_bwd": ("hbm", n_valid * 2 * DENSITY_BYTES),
             "k_appearance": ("hbm", n_app * APP_BYTES),

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NVFI_ABI_VERSION 7
+#define NVFI_ABI_VERSION 8
 
 /* error codes */
 #define NVFI_OK 0
@@ -70,10 +70,13 @@ typedef struct NvfiLinear {
                           per 32-wide K block the TF32 "hi" slab [umma_rows][32] followed by the
                           "lo" (residual) slab, both K-major with the 128-byte swizzle; NULL when
                           the layer only runs on the FP32 SIMT path */
+  const float* ummaT;  /* the same kind of image of W^T (rows = input features: 128, or 32 for the
+                          28-wide first layer; K = 128 outputs), for the input-gradient GEMMs of
+                          the tensor-core backward pass; NULL when never differentiated */
   int32_t in_dim, out_dim; /* logical sizes */
   int32_t k_pad, n_pad;    /* padded sizes: k_pad % 32 == 0, n_pad % 4 == 0 */
   int32_t umma_rows;       /* rows (N) of the image: 128 for hidden layers, 16 for a narrow head */
-  int32_t reserved_;
+  int32_t ummaT_rows;
 } NvfiLinear;
 
 /* Everything the render path reads.  Mirrors the attributes of

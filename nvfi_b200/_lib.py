@@ -12,7 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnvfi_b200.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 VEL_LAYERS = 6
 MAX_MASK_LAYERS = 8
 
@@ -29,8 +29,8 @@ P3 = C.c_void_p * 3
 
 class NvfiLinear(C.Structure):
     _fields_ = [("wt", C.c_void_p), ("bias", C.c_void_p), ("w_rows", C.c_void_p), ("umma", C.c_void_p),
-                ("in_dim", C.c_int32), ("out_dim", C.c_int32), ("k_pad", C.c_int32), ("n_pad", C.c_int32),
-                ("umma_rows", C.c_int32), ("reserved_", C.c_int32)]
+                ("ummaT", C.c_void_p), ("in_dim", C.c_int32), ("out_dim", C.c_int32), ("k_pad", C.c_int32), ("n_pad", C.c_int32),
+                ("umma_rows", C.c_int32), ("ummaT_rows", C.c_int32)]
 
 
 class NvfiField(C.Structure):

@@ -66,7 +66,7 @@ struct TcMlp {
     kphase = 0;
     mode3 = (mode == NVFI_MLP_TF32X3) ? 1 : 0;
     tc::setup(*ctl, n0, n1);
-    is.init(*ctl, *ring);
+    is.init(*ctl, tc::smem_u32(ring->stage[0]), tc::kStages);
   }
   __device__ void finish() { tc::teardown(*ctl, is); }
   template <int ACT>

@@ -90,6 +90,10 @@ class PackedLinear:
         self.umma_rows = (128 if hidden else _round_up(out_dim, 16)) if umma else 0
         self.umma = (torch.zeros((self.k_pad // 32) * 2 * self.umma_rows * 32, device=device,
                                  dtype=torch.float32) if umma else None)
+        # image of W^T (hidden layers that are differentiated): rows = input features
+        self.ummaT_rows = (128 if in_dim == 128 else _round_up(in_dim, 32)) if (umma and diff and hidden) else 0
+        self.ummaT = (torch.zeros((128 // 32) * 2 * self.ummaT_rows * 32, device=device, dtype=torch.float32)
+                      if self.ummaT_rows else None)
         self.track = _Tracked()
 
     def sync(self, w: torch.Tensor, b: Optional[torch.Tensor]):
@@ -106,6 +110,10 @@ class PackedLinear:
         if self.umma is not None:
             L.check(lib.nvfi_pack_linear_umma(wd.data_ptr(), self.umma.data_ptr(), self.out_dim, self.in_dim,
                                               self.umma_rows, self.k_pad, _stream()), "pack_linear_umma")
+        if self.ummaT is not None:
+            wT = wd.t().contiguous()      # (in, out): "out_dim" = input features, K = 128 outputs
+            L.check(lib.nvfi_pack_linear_umma(wT.data_ptr(), self.ummaT.data_ptr(), self.in_dim, self.out_dim,
+                                              self.ummaT_rows, 128, _stream()), "pack_linear_umma(T)")
 
     def fill(self, s: L.NvfiLinear):
         s.wt = self.wt.data_ptr()
@@ -113,6 +121,8 @@ class PackedLinear:
         s.w_rows = _ptr(self.w_rows)
         s.umma = _ptr(self.umma)
         s.umma_rows = self.umma_rows
+        s.ummaT = _ptr(self.ummaT)
+        s.ummaT_rows = self.ummaT_rows
         s.in_dim, s.out_dim, s.k_pad, s.n_pad = self.in_dim, self.out_dim, self.k_pad, self.n_pad
 
     def unpack_grad(self, g_wt: torch.Tensor, g_b: Optional[torch.Tensor], want_bias: bool):

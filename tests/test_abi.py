@@ -44,7 +44,7 @@ def test_struct_layouts_match_c():
     from nvfi_b200 import _lib
     if not any(os.access(os.path.join(p, "gcc"), os.X_OK) for p in os.environ.get("PATH", "").split(":")):
         pytest.skip("gcc not available")
-    probes = [("NvfiLinear", _lib.NvfiLinear, ["umma", "in_dim", "umma_rows"]),
+    probes = [("NvfiLinear", _lib.NvfiLinear, ["umma", "ummaT", "in_dim", "ummaT_rows"]),
               ("NvfiField", _lib.NvfiField, ["grid", "dplane_space", "basis_mat", "vel_net", "gate_lo",
                                              "alpha_volume", "mask_net"]),
               ("NvfiRenderArgs", _lib.NvfiRenderArgs, ["jitter", "chunk_bg", "t", "advect"]),
