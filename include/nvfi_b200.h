@@ -310,6 +310,14 @@ int nvfi_pde_loss(const NvfiField* field, const float* xyzt, const float* va, in
                   double* loss_sums, const NvfiPdeGrads* grads, int32_t want_grad,
                   int32_t* counters, void* stream);
 
+/* ---- development probe -------------------------------------------------------------------
+ * One 128x128x128 TF32 tcgen05 MMA, D[k][n] = sum_m At[k][m] G[m][n], A from tensor memory and
+ * B = G read from the sample-major swizzled shared-memory tile of the tensor-core backward
+ * with caller-supplied descriptor fields (tests/test_gpu_debug_mma.py pins their meaning). */
+int nvfi_debug_mma_mn(const float* At, const float* G, float* Dout, uint32_t lbo_field,
+                      uint32_t sbo_field, uint32_t kstep_bytes, uint32_t layout_type,
+                      uint32_t b_mn_major, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,7 +43,9 @@ namespace nvfi {
 #define AW_STASH_H1 (AW_STASH_H0 + STASH_F)
 #define AW_STASH_F48 (AW_STASH_H1 + STASH_F)    // 64 x 128
 #define AW_TOTAL (AW_STASH_F48 + 64 * NVFI_TM)
-#define WS_CTA_F (VW_TOTAL > AW_TOTAL ? VW_TOTAL : AW_TOTAL)
+// the tensor-core backward (backward_tc.cu) additionally ping-pongs G between two 128x128 scratch tiles
+#define TCW_TOTAL (VW_TOTAL + 2 * STASH_F)
+#define WS_CTA_F (TCW_TOTAL > AW_TOTAL ? TCW_TOTAL : AW_TOTAL)
 #define MAX_RK2_STEPS 32
 
 

@@ -1,0 +1,705 @@
+// RK2 adjoint through the velocity MLP on the tensor cores (tcgen05): the product path of
+// nvfi_render_backward step 4 (k_advect_bwd in backward.cu is the FP32 SIMT verification
+// path).  Math: SURVEY.md Appendix E "RK2 step"; reference: autograd of
+// models/tensorf_keyframe.py:575-611 + models/velocity_field.py:54-98.
+//
+// Per tile of 128 advected samples and per RK2 step (reverse order):
+//   F   recompute both weight-net evaluations on the tensor cores (mlp_tc.cuh), stashing the
+//       pre-activations h_l[m][n] of the 5 hidden layers in a per-CTA L2-resident scratch
+//   B   for each evaluation, walk the layers in reverse.  With G_l = dL/dh_l (128 samples x
+//       128 units), A_{l-1} = silu(h_{l-1}):
+//         G_{l-1}[m][k] = (sum_n G_l[m][n] W_l[n][k]) silu'(h_{l-1}[m][k])   reduction over UNITS
+//         dW_l^T [k][n] = sum_m A_{l-1}[m][k] G_l[m][n]                      reduction over SAMPLES
+//       Every GEMM is a K-major tcgen05.mma (MN-major TF32 operands need a second swizzle of
+//       the same data, which shared memory has no room for):
+//         dX: A = G_l in TENSOR MEMORY (lane = sample, column = unit — written there straight
+//             from the previous epilogue's registers), B = W_l^T image block from the ring:
+//             the forward machinery with other weights and another epilogue;
+//         dW: A = A_{l-1}^T in tensor memory (lane = input unit, column = sample), built by
+//             reading the stash TRANSPOSED — a coalesced global read —, B = G_l^T in shared
+//             memory (row = unit, 128-byte rows of 32 samples, 128B swizzle), built the same
+//             way from a per-CTA global copy of G_l.  The L2 round trip IS the transpose.
+//       Both accumulate in TMEM (D0 = dX, D1 = dW^T); the epilogue turns D0 into G_{l-1}
+//       (registers -> global copy -> TMEM) and adds D1 to the CTA's partial weight gradient.
+//   The 6-wide head layer and the position-encoding chain rule are FP32 SIMT (tiny).
+// All GEMMs use the 3-term TF32 split (FP32-grade) unless the single-pass mode is selected.
+#include "backward_common.cuh"
+#include "mlp_tc.cuh"
+
+namespace nvfi {
+namespace tcb {
+
+constexpr int NT = tc::kThreads;            // 512 worker threads (+ the issuer warp)
+constexpr uint32_t kBwdStages = 2;          // ring depth: shared memory is needed for G
+constexpr int kLayerF = NVFI_TM * NVFI_TM;  // 16384 floats
+
+// per-CTA global workspace (float offsets)
+constexpr int TW_DW1 = 0;                       // dW^T of layers 1..4: [k][n], 4 x 16384
+constexpr int TW_DW0 = 4 * kLayerF;             // layer 0: [k < 32][n]
+constexpr int TW_HEAD = TW_DW0 + 32 * NVFI_TM;  // head: [k][8]
+constexpr int TW_B = TW_HEAD + NVFI_TM * 8;     // biases [6][128]
+constexpr int TW_PART_F = TW_B + 6 * NVFI_TM;   // floats to zero / reduce
+constexpr int TW_STASH = TW_PART_F;             // [2 evals][5 layers][m][n]
+constexpr int TW_XSTEPS = TW_STASH + 10 * kLayerF;
+constexpr int TW_GBUF = TW_XSTEPS + MAX_RK2_STEPS * 3 * NVFI_TM;   // [2][m][n] copies of G_l
+constexpr int TW_TOTAL = TW_GBUF + 2 * kLayerF;
+
+struct BwdTile {
+  float x0[3][NVFI_TM];
+  float xm[3][NVFI_TM];
+  float gbar[3][NVFI_TM];
+  float gm[3][NVFI_TM];
+  float w0[6][NVFI_TM];
+  float w1[6][NVFI_TM];
+  float gout[6][NVFI_TM];   // in: dL/d(basis weights); out (rows 0..2): dL/d(x, y, z) of the eval input
+  float tvec[NVFI_TM];
+  float w5s[6][NVFI_TM];    // head weights W5[n][k]
+  unsigned char gate0[NVFI_TM], gate1[NVFI_TM], reverted[NVFI_TM];
+  int gidx[NVFI_TM];
+  int q_idx[NVFI_TM + NT];
+  int warp_cnt[2][NT / 32];
+  int batch;
+};
+
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void red_add(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ float silu_d(float h) {   // SiLU'(h)
+  const float s = 1.f / (1.f + __expf(-h));
+  return s * (1.f + h * (1.f - s));
+}
+__device__ __forceinline__ float silu_v(float h) { return h / (1.f + __expf(-h)); }
+
+// Thread (row r, 32-wide K block h): write 32 values of row r, columns [32 h, +32) of a
+// 128 x 128 FP32 operand tile, split hi/lo.  Layout: four K blocks of 16 KB, rows of 128 bytes,
+// 8-row groups of 1 KB, 16-byte chunks XOR-swizzled with the row (K-major SWIZZLE_128B).
+__device__ __forceinline__ void op_store_row32(unsigned char* t_hi, unsigned char* t_lo, int r, int h,
+                                               const float v[32], int mode3) {
+  const uint32_t row = (uint32_t)((h << 14) + ((r >> 3) << 10) + ((r & 7) << 7));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 hi, lo;
+    float t;
+    t = __uint_as_float(tc::to_tf32(v[4 * j + 0])); hi.x = t; lo.x = v[4 * j + 0] - t;
+    t = __uint_as_float(tc::to_tf32(v[4 * j + 1])); hi.y = t; lo.y = v[4 * j + 1] - t;
+    t = __uint_as_float(tc::to_tf32(v[4 * j + 2])); hi.z = t; lo.z = v[4 * j + 2] - t;
+    t = __uint_as_float(tc::to_tf32(v[4 * j + 3])); hi.w = t; lo.w = v[4 * j + 3] - t;
+    const uint32_t off = row + (uint32_t)((j ^ (r & 7)) << 4);
+    *reinterpret_cast<float4*>(t_hi + off) = hi;
+    if (mode3) *reinterpret_cast<float4*>(t_lo + off) = lo;
+  }
+}
+
+// Thread (TMEM lane, 32-column group h): store 32 values into the TMEM operand region, hi/lo.
+__device__ __forceinline__ void tm_store32(uint32_t tb, uint32_t lane_base, int h, const float v[32],
+                                           int mode3) {
+  uint32_t hi[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) hi[i] = tc::to_tf32(v[i]);
+  tc::tmem_st32(tb + lane_base + tc::kColAhi + (uint32_t)(h * 32), hi);
+  if (mode3) {
+    uint32_t lo[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
+    tc::tmem_st32(tb + lane_base + tc::kColAlo + (uint32_t)(h * 32), lo);
+  }
+}
+
+// ---- issuer warp ----------------------------------------------------------------------------
+// dX of layer l:  D0[m][k] = sum_n G[m][n] Wt[k][n]   A = G in TMEM, B = W^T image blocks (ring)
+__device__ __forceinline__ void issue_dx(tc::Ctl& c, tc::Issuer& is, int layer, int mode3) {
+  const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  const uint32_t nx = (layer == 0) ? 32u : 128u;
+  const uint32_t idesc = tc::instr_desc_tf32((int)nx);
+  const uint32_t d0 = is.tb + tc::kColD;
+  for (uint32_t kb = 0; kb < 4; ++kb) {
+    tc::ring_top_up(c, is, mode3);
+    tc::mbar_wait(&c.full[is.c_stage], is.c_round & 1);
+    tc::tc_fence_after();
+    const uint32_t st = is.ring_u32 + is.c_stage * (uint32_t)tc::kStageBytes;
+    const uint32_t w_hi = ((st >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t w_lo = (((st + nx * 128u) >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t a_hi = is.tb + tc::kColAhi + kb * 32u, a_lo = is.tb + tc::kColAlo + kb * 32u;
+    if (tc::elect_one()) {
+#pragma unroll
+      for (uint32_t ks = 0; ks < 4; ++ks) {
+        const uint64_t wh = ((uint64_t)desc_hi << 32) | (uint64_t)(w_hi + ks * 2u);
+        tc::mma_tf32_ts(d0, a_hi + ks * 8u, wh, idesc, (kb | ks) ? 1u : 0u);
+        if (mode3) {
+          const uint64_t wl = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo + ks * 2u);
+          tc::mma_tf32_ts(d0, a_hi + ks * 8u, wl, idesc, 1u);
+          tc::mma_tf32_ts(d0, a_lo + ks * 8u, wh, idesc, 1u);
+        }
+      }
+      tc::tc_commit(&c.empty[is.c_stage]);
+      if (kb == 3) tc::tc_commit(&c.dbar);
+    }
+    __syncwarp();
+    if (++is.c_stage == is.n_stages) {
+      is.c_stage = 0;
+      ++is.c_round;
+    }
+    --is.in_flight;
+  }
+}
+// dW of layer l:  D1[k][n] = sum_m A^T[k][m] G^T[n][m]   A = A^T in TMEM, B = G^T in shared memory
+__device__ __forceinline__ void issue_dw(tc::Ctl& c, tc::Issuer& is, uint32_t gt_hi, uint32_t gt_lo,
+                                         int mode3) {
+  const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  const uint32_t idesc = tc::instr_desc_tf32(128);
+  const uint32_t d1 = is.tb + tc::kColD + 128u;
+  const uint32_t gh = ((gt_hi >> 4) & 0x3FFFu) | (1u << 16), gl = ((gt_lo >> 4) & 0x3FFFu) | (1u << 16);
+  if (tc::elect_one()) {
+#pragma unroll 4
+    for (uint32_t ks = 0; ks < 16; ++ks) {   // 4 K blocks (16 KB apart) x 4 steps of 8 samples (32 B)
+      const uint32_t step = (ks >> 2) * 1024u + (ks & 3u) * 2u;
+      const uint64_t bh = ((uint64_t)desc_hi << 32) | (uint64_t)(gh + step);
+      const uint32_t a_hi = is.tb + tc::kColAhi + ks * 8u, a_lo = is.tb + tc::kColAlo + ks * 8u;
+      tc::mma_tf32_ts(d1, a_hi, bh, idesc, ks ? 1u : 0u);
+      if (mode3) {
+        const uint64_t bl = ((uint64_t)desc_hi << 32) | (uint64_t)(gl + step);
+        tc::mma_tf32_ts(d1, a_hi, bl, idesc, 1u);
+        tc::mma_tf32_ts(d1, a_lo, bh, idesc, 1u);
+      }
+    }
+    tc::tc_commit(&c.dbar);
+  }
+  __syncwarp();
+}
+
+// ---- backward through one weight-net evaluation -------------------------------------------
+// In: T.gout[n][m] = dL/d(basis weights), stash = the evaluation's pre-activations, (xs,ys,zs)[m]
+// and tval = its input.  Out: T.gout[0..2][m] = dL/d(x, y, z) through the network input; weight
+// and bias gradients added to the CTA's partials in `ws`.  Whole CTA (11 block barriers).
+__device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned char* gt_hi,
+                            unsigned char* gt_lo, float* __restrict__ ws, const float* stash,
+                            const float* xs, const float* ys, const float* zs, float tval,
+                            uint32_t& dphase, int mode3) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == tc::kIssuerWarp) {
+    const uint32_t gh = tc::uniform(tc::smem_u32(gt_hi)), gl = tc::uniform(tc::smem_u32(gt_lo));
+    __syncthreads();   // (A) head done: G_4 in TMEM and in the global copy
+#pragma unroll 1
+    for (int l = 4; l >= 0; --l) {
+      tc::tc_fence_after();
+      issue_dx(c, is, l, mode3);
+      __syncthreads();   // (B) G_l^T in shared memory, A_{l-1}^T in TMEM
+      tc::tc_fence_after();
+      issue_dw(c, is, gh, gl, mode3);
+      __syncthreads();   // (C) G_{l-1} in TMEM and in the global copy
+    }
+    dphase += 10;
+    return;
+  }
+  const int q = warp & 3, h = warp >> 2;
+  const int m = q * 32 + lane;                 // sample of this thread in the sample-major steps
+  const int k = m;                             // unit   of this thread in the unit-major steps
+  const uint32_t tb = c.tmem_base;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  float* gbuf = ws + TW_GBUF;
+
+  // ---- head layer (128 -> 6), FP32 SIMT: G_4 -> TMEM + global copy; dW5, db5
+  {
+    float gw[6];
+#pragma unroll
+    for (int n = 0; n < 6; ++n) gw[n] = T.gout[n][m];
+    const float4* hp = reinterpret_cast<const float4*>(stash + ((size_t)4 * NVFI_TM + m) * NVFI_TM + h * 32);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 hv = __ldcg(hp + j);
+      const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = h * 32 + j * 4 + i;
+        float s = 0.f;
+#pragma unroll
+        for (int n = 0; n < 6; ++n) s = fmaf(gw[n], T.w5s[n][kk], s);
+        v[j * 4 + i] = s * silu_d(hh[i]);
+      }
+    }
+    tm_store32(tb, lane_base, h, v, mode3);
+    float4* gp = reinterpret_cast<float4*>(gbuf + (size_t)m * NVFI_TM + h * 32);   // copy 0 = G_4
+#pragma unroll
+    for (int j = 0; j < 8; ++j) __stcg(gp + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+    // dW5^T[k][n] = sum_m silu(h4[m][k]) gout[n][m], this thread: unit k, samples [32 h, +32)
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {
+      const int mm = h * 32 + i;
+      const float a = silu_v(__ldcg(stash + ((size_t)4 * NVFI_TM + mm) * NVFI_TM + k));
+#pragma unroll
+      for (int n = 0; n < 6; ++n) acc[n] = fmaf(a, T.gout[n][mm], acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < 6; ++n) red_add(ws + TW_HEAD + k * 8 + n, acc[n]);
+    if (tid < 6) {
+      float s = 0.f;
+      for (int mm = 0; mm < NVFI_TM; ++mm) s += T.gout[tid][mm];
+      red_add(ws + TW_B + 5 * NVFI_TM + tid, s);
+    }
+    tc::tmem_st_wait();
+  }
+  tc::tc_fence_before();
+  __syncthreads();   // (A)
+
+#pragma unroll 1
+  for (int l = 4; l >= 0; --l) {
+    const float* gsrc = gbuf + (size_t)((4 - l) & 1) * kLayerF;        // G_l
+    float* gdst = gbuf + (size_t)((5 - l) & 1) * kLayerF;              // G_{l-1}
+    // ---- while the dX MMAs run: G_l^T into shared memory (unit n = k, samples [32 h, +32)),
+    //      bias gradient db_l[n] = sum_m G_l[m][n]
+    {
+      float v[32];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = __ldcg(gsrc + (size_t)(h * 32 + i) * NVFI_TM + k);
+        s += v[i];
+      }
+      op_store_row32(gt_hi, gt_lo, k, h, v, mode3);
+      red_add(ws + TW_B + l * NVFI_TM + k, s);
+      fence_async_smem();
+    }
+    tc::mbar_wait(&c.dbar, dphase & 1);   // dX accumulator
+    ++dphase;
+    tc::tc_fence_after();
+    // ---- dX epilogue (sample-major): G_{l-1} in registers, global copy; or the encoder chain rule
+    float gnew[32];
+    if (l > 0) {
+      tc::tmem_ld32(tb + lane_base + tc::kColD + (uint32_t)(h * 32), gnew);
+      const float4* hp = reinterpret_cast<const float4*>(stash + ((size_t)(l - 1) * NVFI_TM + m) * NVFI_TM + h * 32);
+      float4* gp = reinterpret_cast<float4*>(gdst + (size_t)m * NVFI_TM + h * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 hv = __ldcg(hp + j);
+        gnew[4 * j + 0] *= silu_d(hv.x);
+        gnew[4 * j + 1] *= silu_d(hv.y);
+        gnew[4 * j + 2] *= silu_d(hv.z);
+        gnew[4 * j + 3] *= silu_d(hv.w);
+        __stcg(gp + j, make_float4(gnew[4 * j], gnew[4 * j + 1], gnew[4 * j + 2], gnew[4 * j + 3]));
+      }
+    } else if (h == 0) {
+      // dL/d(encoding) -> dL/d(x, y, z)  (encoder tangents)
+      tc::tmem_ld32(tb + lane_base + tc::kColD, gnew);
+      const float qv[3] = {xs[m], ys[m], zs[m]};
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        float s1, c1, s2, c2, s4, c4;
+        sincosf(qv[i], &s1, &c1);
+        sincosf(qv[i] * 2.f, &s2, &c2);
+        sincosf(qv[i] * 4.f, &s4, &c4);
+        T.gout[i][m] = gnew[i] + gnew[4 + i] * c1 - gnew[8 + i] * s1 +
+                       2.f * (gnew[12 + i] * c2 - gnew[16 + i] * s2) +
+                       4.f * (gnew[20 + i] * c4 - gnew[24 + i] * s4);
+      }
+    }
+    // ---- A_{l-1}^T into the TMEM operand region (the dX MMAs have finished reading G_l there)
+    {
+      float v[32];
+      if (l > 0) {
+        const float* sp = stash + (size_t)(l - 1) * kLayerF + k;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = silu_v(__ldcg(sp + (size_t)(h * 32 + i) * NVFI_TM));
+      } else {
+        // encoding^T (models/base_network.py:42-54): unit k < 28 of samples [32 h, +32)
+        const int grp = k >> 2, ci = k & 3;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int mm = h * 32 + i;
+          const float qv = (ci == 0) ? xs[mm] : (ci == 1) ? ys[mm] : (ci == 2) ? zs[mm] : tval;
+          float r = 0.f;
+          if (k < 28) {
+            const float f = (grp <= 2) ? 1.f : ((grp <= 4) ? 2.f : 4.f);
+            if (grp == 0) r = qv;
+            else if (grp & 1) r = sinf(qv * f);
+            else r = cosf(qv * f);
+          }
+          v[i] = r;
+        }
+      }
+      tm_store32(tb, lane_base, h, v, mode3);
+      tc::tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();   // (B)
+    tc::mbar_wait(&c.dbar, dphase & 1);   // dW accumulator
+    ++dphase;
+    tc::tc_fence_after();
+    // ---- dW^T flush (unit-major) and G_{l-1} into the TMEM operand region (sample-major)
+    if (l > 0 || q == 0) {
+      float dwv[32];
+      tc::tmem_ld32(tb + lane_base + tc::kColD + 128u + (uint32_t)(h * 32), dwv);
+      float4* wp = reinterpret_cast<float4*>(ws + ((l > 0) ? (TW_DW1 + (l - 1) * kLayerF) : TW_DW0) +
+                                             k * NVFI_TM + h * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 o = wp[j];
+        o.x += dwv[4 * j + 0];
+        o.y += dwv[4 * j + 1];
+        o.z += dwv[4 * j + 2];
+        o.w += dwv[4 * j + 3];
+        wp[j] = o;
+      }
+    }
+    if (l > 0) {
+      tm_store32(tb, lane_base, h, gnew, mode3);
+      tc::tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();   // (C)
+  }
+}
+
+// v = basis(w, x): dL/dw and the explicit dL/dx from dL/dv (as in backward.cu)
+__device__ __forceinline__ void basis_bwd(const float w[6], float x, float y, float z, const float gv[3],
+                                          float gw[6], float gxe[3]) {
+  gw[0] = gv[0];
+  gw[1] = gv[1];
+  gw[2] = gv[2];
+  gw[3] = gv[1] * z - gv[2] * y;
+  gw[4] = -gv[0] * z + gv[2] * x;
+  gw[5] = gv[0] * y - gv[1] * x;
+  gxe[0] = -w[5] * gv[1] + w[4] * gv[2];
+  gxe[1] = w[5] * gv[0] - w[3] * gv[2];
+  gxe[2] = -w[4] * gv[0] + w[3] * gv[1];
+}
+
+__global__ void __launch_bounds__(tc::kLaunchThreads, 1)
+    k_advect_bwd_tc(const __grid_constant__ NvfiField F, const NvfiRenderArgs A, const NvfiRenderBuffers B,
+                    const NvfiRenderGrads D, int S, long long total, int n_batches, int mode) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* p = smem_raw;
+  {
+    const uint32_t a = tc::smem_u32(p);
+    p += (1024u - (a & 1023u)) & 1023u;
+  }
+  unsigned char* ring = p;                                   // kBwdStages x 32 KB
+  unsigned char* g_hi = ring + kBwdStages * tc::kStageBytes; // G^T hi: 64 KB, 1024-aligned
+  unsigned char* g_lo = g_hi + 65536;                        // G^T lo
+  tc::Ctl& ctl = *reinterpret_cast<tc::Ctl*>(g_lo + 65536);
+  BwdTile& T = *reinterpret_cast<BwdTile*>(reinterpret_cast<unsigned char*>(&ctl) + sizeof(tc::Ctl));
+  float* ws = D.workspace + (size_t)blockIdx.x * WS_CTA_F;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mode3 = (mode == NVFI_MLP_TF32X3) ? 1 : 0;
+
+  // uniform RK2 schedule of this render call (models/tensorf_keyframe.py:577-609)
+  float sched_dt[MAX_RK2_STEPS], sched_t[MAX_RK2_STEPS];
+  int n_steps = 0;
+  {
+    float off = __fsub_rn(A.t, A.base_time), tc_ = A.t;
+    while (fabsf(off) > 0.f && n_steps < MAX_RK2_STEPS) {
+      float dt = fminf(fabsf(off), F.dt_max);
+      dt = (off > 0.f) ? dt : -dt;
+      sched_dt[n_steps] = dt;
+      sched_t[n_steps] = tc_;
+      off = __fsub_rn(off, dt);
+      tc_ = __fsub_rn(tc_, dt);
+      ++n_steps;
+    }
+  }
+
+  tc::setup(ctl, F.vel_net, nullptr);
+  if (tid == 0) {   // weight segments in the order one tile consumes them
+    int n = 0;
+    for (int k = 0; k + 1 < n_steps; ++k) {
+      ctl.prog[n++] = tc::SEG_FWD0;
+      ctl.prog[n++] = tc::SEG_FWD0;
+    }
+    for (int k = 0; k < n_steps; ++k) {
+      ctl.prog[n++] = tc::SEG_FWD0;
+      ctl.prog[n++] = tc::SEG_FWD0;
+      ctl.prog[n++] = tc::SEG_BWD0;
+      ctl.prog[n++] = tc::SEG_BWD0;
+    }
+    ctl.prog_len = (uint32_t)n;
+  }
+  for (int i = tid; i < 6 * NVFI_TM; i += blockDim.x) {
+    const int n = i / NVFI_TM, kk = i - n * NVFI_TM;
+    T.w5s[n][kk] = __ldg(F.vel_net[5].wt + (size_t)kk * F.vel_net[5].n_pad + n);
+  }
+  for (int i = tid; i < TW_PART_F; i += blockDim.x) ws[i] = 0.f;
+  __syncthreads();
+  tc::Issuer is;
+  is.init(ctl, tc::smem_u32(ring), kBwdStages);
+  uint32_t dphase = 0, kphase = 0;
+
+  int sub = NVFI_SUBS;
+  long long batch_base = 0;
+  bool exhausted = false;
+  int qc = 0, par = 0;
+  unsigned long long n_done = 0;
+  float* stash0 = ws + TW_STASH;
+  float* stash1 = ws + TW_STASH + 5 * kLayerF;
+  float* xsteps = ws + TW_XSTEPS;
+
+  auto net_fwd = [&](float* wout, const float* xs, const float* ys, const float* zs, float* stash) {
+    if (stash)
+      tc::vel_net_tile_tc<ACT_SILU, true>(ctl, is, 0, wout, xs, ys, zs, T.tvec, dphase, kphase, mode3, stash);
+    else
+      tc::vel_net_tile_tc<ACT_SILU, false>(ctl, is, 0, wout, xs, ys, zs, T.tvec, dphase, kphase, mode3);
+  };
+
+  for (;;) {
+    while (qc < NVFI_TM && !exhausted) {
+      if (sub == NVFI_SUBS) {
+        if (tid == 0) T.batch = atomicAdd(&B.counters[3], 1);
+        __syncthreads();
+        const int b = T.batch;
+        __syncthreads();
+        if (b >= n_batches) {
+          exhausted = true;
+          break;
+        }
+        batch_base = (long long)b * (NVFI_SUBS * NT);
+        sub = 0;
+      }
+      const long long idx = batch_base + (long long)sub * NT + tid;
+      ++sub;
+      bool push = false;
+      if (tid < NT && idx < total && B.valid[idx]) {
+        const float g0 = D.g_x_adv[idx * 3], g1 = D.g_x_adv[idx * 3 + 1], g2 = D.g_x_adv[idx * 3 + 2];
+        push = (g0 != 0.f) | (g1 != 0.f) | (g2 != 0.f);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, push);
+      if (lane == 0 && warp < NT / 32) T.warp_cnt[par][warp] = __popc(bal);
+      const int tot = __syncthreads_count(push);
+      if (push) {
+        int pos = qc + __popc(bal & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) pos += T.warp_cnt[par][w];
+        T.q_idx[pos] = (int)idx;
+      }
+      qc += tot;
+      par ^= 1;
+    }
+    if (qc == 0) break;
+    __syncthreads();
+    const int n = min(NVFI_TM, qc);
+    const int start = qc - n;
+    qc = start;
+    n_done += n;
+    // ---- load the tile: start position (sampler recompute) and upstream gradient
+    if (tid < NVFI_TM) {
+      const bool live = tid < n;
+      const long long gi = live ? T.q_idx[start + tid] : 0;
+      T.gidx[tid] = (int)gi;
+      float xn[3] = {0.f, 0.f, 0.f};
+      if (live) {
+        const long long ray = gi / S;
+        const int s = (int)(gi - ray * S);
+        const float o[3] = {__ldg(A.rays_o + ray * 3), __ldg(A.rays_o + ray * 3 + 1),
+                            __ldg(A.rays_o + ray * 3 + 2)};
+        const float d[3] = {__ldg(A.rays_d + ray * 3), __ldg(A.rays_d + ray * 3 + 1),
+                            __ldg(A.rays_d + ray * 3 + 2)};
+        const bool inside = B.chunk_inside[ray / A.ray_chunk] != 0;
+        const float tmin = ray_tmin(F, o, d, inside);
+        const bool train = A.jitter != nullptr;
+        const float u = train ? __ldg(A.jitter + ray) : 0.f;
+        sample_point(F, o, d, sample_z(tmin, F.step_size, s, u, train), xn);
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        T.x0[a][tid] = xn[a];
+        T.gbar[a][tid] = live ? D.g_x_adv[gi * 3 + a] : 0.f;
+      }
+    }
+    __syncthreads();
+    // ---- forward sweep over all but the last step, remembering the step start positions
+    for (int k = 0; k + 1 < n_steps; ++k) {
+      const float dt = sched_dt[k], tcur = sched_t[k], hdt = 0.5f * dt;
+      if (tid < NVFI_TM) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) xsteps[(k * 3 + a) * NVFI_TM + tid] = T.x0[a][tid];
+        T.tvec[tid] = tcur;
+      }
+      __syncthreads();
+      net_fwd(&T.w0[0][0], T.x0[0], T.x0[1], T.x0[2], nullptr);
+      if (tid < NVFI_TM) {
+        const int m = tid;
+        const float x = T.x0[0][m], y = T.x0[1][m], z = T.x0[2][m];
+        float v[3] = {0.f, 0.f, 0.f};
+        if (!gate_outside(F, x, y, z)) {
+          const float w[6] = {T.w0[0][m], T.w0[1][m], T.w0[2][m], T.w0[3][m], T.w0[4][m], T.w0[5][m]};
+          basis_velocity(w, x, y, z, v);
+        }
+        T.xm[0][m] = __fsub_rn(x, __fmul_rn(hdt, v[0]));
+        T.xm[1][m] = __fsub_rn(y, __fmul_rn(hdt, v[1]));
+        T.xm[2][m] = __fsub_rn(z, __fmul_rn(hdt, v[2]));
+        T.tvec[m] = __fsub_rn(tcur, hdt);
+      }
+      __syncthreads();
+      net_fwd(&T.w1[0][0], T.xm[0], T.xm[1], T.xm[2], nullptr);
+      if (tid < NVFI_TM) {
+        const int m = tid;
+        const float xm = T.xm[0][m], ym = T.xm[1][m], zm = T.xm[2][m];
+        float v[3] = {0.f, 0.f, 0.f};
+        if (!gate_outside(F, xm, ym, zm)) {
+          const float w[6] = {T.w1[0][m], T.w1[1][m], T.w1[2][m], T.w1[3][m], T.w1[4][m], T.w1[5][m]};
+          basis_velocity(w, xm, ym, zm, v);
+        }
+        const float x = T.x0[0][m], y = T.x0[1][m], z = T.x0[2][m];
+        float nx = __fsub_rn(x, __fmul_rn(dt, v[0]));
+        float ny = __fsub_rn(y, __fmul_rn(dt, v[1]));
+        float nz = __fsub_rn(z, __fmul_rn(dt, v[2]));
+        if (F.vel_gate == NVFI_GATE_SUR && gate_outside(F, nx, ny, nz)) {
+          nx = x;
+          ny = y;
+          nz = z;
+        }
+        T.x0[0][m] = nx;
+        T.x0[1][m] = ny;
+        T.x0[2][m] = nz;
+      }
+      __syncthreads();
+    }
+    // ---- reverse sweep
+    for (int k = n_steps - 1; k >= 0; --k) {
+      const float dt = sched_dt[k], tcur = sched_t[k], hdt = 0.5f * dt;
+      const float tmid = __fsub_rn(tcur, hdt);
+      if (tid < NVFI_TM) {
+        if (k < n_steps - 1) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) T.x0[a][tid] = xsteps[(k * 3 + a) * NVFI_TM + tid];
+        }
+        T.tvec[tid] = tcur;
+      }
+      __syncthreads();
+      net_fwd(&T.w0[0][0], T.x0[0], T.x0[1], T.x0[2], stash0);
+      if (tid < NVFI_TM) {
+        const int m = tid;
+        const float x = T.x0[0][m], y = T.x0[1][m], z = T.x0[2][m];
+        float v[3] = {0.f, 0.f, 0.f};
+        const bool out0 = gate_outside(F, x, y, z);
+        T.gate0[m] = out0;
+        if (!out0) {
+          const float w[6] = {T.w0[0][m], T.w0[1][m], T.w0[2][m], T.w0[3][m], T.w0[4][m], T.w0[5][m]};
+          basis_velocity(w, x, y, z, v);
+        }
+        T.xm[0][m] = __fsub_rn(x, __fmul_rn(hdt, v[0]));
+        T.xm[1][m] = __fsub_rn(y, __fmul_rn(hdt, v[1]));
+        T.xm[2][m] = __fsub_rn(z, __fmul_rn(hdt, v[2]));
+        T.tvec[m] = tmid;
+      }
+      __syncthreads();
+      net_fwd(&T.w1[0][0], T.xm[0], T.xm[1], T.xm[2], stash1);
+      // adjoint of x1 = x0 - dt v1(m)
+      if (tid < NVFI_TM) {
+        const int m = tid;
+        const float xm = T.xm[0][m], ym = T.xm[1][m], zm = T.xm[2][m];
+        const bool out1 = gate_outside(F, xm, ym, zm);
+        const float w[6] = {T.w1[0][m], T.w1[1][m], T.w1[2][m], T.w1[3][m], T.w1[4][m], T.w1[5][m]};
+        float v[3] = {0.f, 0.f, 0.f};
+        if (!out1) basis_velocity(w, xm, ym, zm, v);
+        const float x = T.x0[0][m], y = T.x0[1][m], z = T.x0[2][m];
+        const float nx = __fsub_rn(x, __fmul_rn(dt, v[0]));
+        const float ny = __fsub_rn(y, __fmul_rn(dt, v[1]));
+        const float nz = __fsub_rn(z, __fmul_rn(dt, v[2]));
+        const bool rev = (F.vel_gate == NVFI_GATE_SUR) && gate_outside(F, nx, ny, nz);
+        T.gate1[m] = out1;
+        T.reverted[m] = rev;
+        float gw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gxe[3] = {0.f, 0.f, 0.f};
+        if (!rev && !out1) {
+          const float gv[3] = {-dt * T.gbar[0][m], -dt * T.gbar[1][m], -dt * T.gbar[2][m]};
+          basis_bwd(w, xm, ym, zm, gv, gw, gxe);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) T.gout[i][m] = gw[i];
+        T.gm[0][m] = gxe[0];
+        T.gm[1][m] = gxe[1];
+        T.gm[2][m] = gxe[2];
+      }
+      __syncthreads();
+      bwd_eval_tc(ctl, is, T, g_hi, g_lo, ws, stash1, T.xm[0], T.xm[1], T.xm[2], tmid, dphase, mode3);
+      // adjoint of m = x0 - dt/2 v0(x0)
+      if (tid < NVFI_TM) {
+        const int m = tid;
+        float gmv[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) gmv[a] = T.gm[a][m] + T.gout[a][m];
+        float gx0[3] = {T.gbar[0][m] + gmv[0], T.gbar[1][m] + gmv[1], T.gbar[2][m] + gmv[2]};
+        float gw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (!T.gate0[m]) {
+          const float w[6] = {T.w0[0][m], T.w0[1][m], T.w0[2][m], T.w0[3][m], T.w0[4][m], T.w0[5][m]};
+          const float gv[3] = {-hdt * gmv[0], -hdt * gmv[1], -hdt * gmv[2]};
+          float gxe[3];
+          basis_bwd(w, T.x0[0][m], T.x0[1][m], T.x0[2][m], gv, gw, gxe);
+          gx0[0] += gxe[0];
+          gx0[1] += gxe[1];
+          gx0[2] += gxe[2];
+        }
+        T.gbar[0][m] = gx0[0];
+        T.gbar[1][m] = gx0[1];
+        T.gbar[2][m] = gx0[2];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) T.gout[i][m] = gw[i];
+      }
+      __syncthreads();
+      bwd_eval_tc(ctl, is, T, g_hi, g_lo, ws, stash0, T.x0[0], T.x0[1], T.x0[2], tcur, dphase, mode3);
+      if (tid < NVFI_TM) {
+        const int m = tid;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) T.gbar[a][m] += T.gout[a][m];
+      }
+      __syncthreads();
+    }
+  }
+  tc::teardown(ctl, is);
+  if (tid == 0 && n_done)
+    atomicAdd(reinterpret_cast<unsigned long long*>(B.counters + 10), n_done);
+}
+
+// g[e] += sum over CTAs of ws[c][off + e]
+__global__ void k_reduce_plain(const float* __restrict__ ws, int n_cta, int off, int n,
+                               float* __restrict__ g) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float s = 0.f;
+  for (int c = 0; c < n_cta; ++c) s += ws[(size_t)c * WS_CTA_F + off + e];
+  g[e] += s;
+}
+
+}  // namespace tcb
+}  // namespace nvfi
+
+using namespace nvfi;
+
+static_assert(tcb::TW_TOTAL <= WS_CTA_F, "per-CTA workspace of the tensor-core backward exceeds WS_CTA_F");
+
+extern "C" int nvfi_launch_advect_bwd_tc(const NvfiField* F, const NvfiRenderArgs* A,
+                                         const NvfiRenderBuffers* B, const NvfiRenderGrads* D, int S,
+                                         long long total, int sms, int mode, cudaStream_t st) {
+  for (int l = 0; l < NVFI_VEL_LAYERS; ++l) {
+    if (!F->vel_net[l].umma) return NVFI_EINVAL;
+    if (l < NVFI_VEL_LAYERS - 1 && (!F->vel_net[l].ummaT || F->vel_net[l].ummaT_rows != (l == 0 ? 32 : 128)))
+      return NVFI_EINVAL;
+  }
+  if (F->vel_net[5].n_pad != 8) return NVFI_EUNSUPPORTED;
+  const size_t smem = 1024 + (size_t)tcb::kBwdStages * tc::kStageBytes + 2 * 65536 + sizeof(tc::Ctl) +
+                      sizeof(tcb::BwdTile);
+  static size_t cached = 0;
+  if (smem > cached) {
+    NVFI_CUDA_OK(cudaFuncSetAttribute(tcb::k_advect_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    cached = smem;
+  }
+  const int per_batch = NVFI_SUBS * tcb::NT;
+  const int n_batches = (int)((total + per_batch - 1) / per_batch);
+  const int grid = n_batches < sms ? n_batches : sms;
+  NVFI_LAUNCH(tcb::k_advect_bwd_tc, grid, tc::kLaunchThreads, smem, st, *F, *A, *B, *D, S, total, n_batches, mode);
+  NVFI_CUDA_OK(cudaGetLastError());
+  for (int l = 1; l <= 4; ++l)
+    NVFI_LAUNCH(tcb::k_reduce_plain, tcb::kLayerF / 256, 256, 0, st, D->workspace, grid,
+                tcb::TW_DW1 + (l - 1) * tcb::kLayerF, tcb::kLayerF, D->g_vel_w[l]);
+  NVFI_LAUNCH(tcb::k_reduce_plain, 32 * NVFI_TM / 256, 256, 0, st, D->workspace, grid, tcb::TW_DW0,
+              32 * NVFI_TM, D->g_vel_w[0]);
+  NVFI_LAUNCH(tcb::k_reduce_plain, NVFI_TM * 8 / 256, 256, 0, st, D->workspace, grid, tcb::TW_HEAD,
+              NVFI_TM * 8, D->g_vel_w[5]);
+  for (int l = 0; l < 5; ++l)
+    NVFI_LAUNCH(tcb::k_reduce_plain, 1, 128, 0, st, D->workspace, grid, tcb::TW_B + l * NVFI_TM, NVFI_TM,
+                D->g_vel_b[l]);
+  NVFI_LAUNCH(tcb::k_reduce_plain, 1, 128, 0, st, D->workspace, grid, tcb::TW_B + 5 * NVFI_TM, 8, D->g_vel_b[5]);
+  return (int)cudaGetLastError();
+}

@@ -93,3 +93,33 @@ def test_modes_agree_on_large_batch(model, g):
     finally:
         engine.set_mlp_mode(prev)
     assert rel_err(got.cpu(), ref.cpu()) < 2e-5
+
+
+@pytest.mark.parametrize("i", range(2))
+def test_train_grads_modes(g, mode, i):
+    """Backward pass (RK2 adjoint through the velocity MLP) in every arithmetic mode against the
+    gradients the reference itself produced."""
+    import numpy as np
+    from tests.helpers import norm_rel_err, scalar_loss
+    case = g.case(f"train{i}")
+    model = build_model(g, requires_grad=True)
+    f = model.nvfi
+    f.train()
+    o, d = g.rays()
+    bg = torch.from_numpy(case["random_bg"].astype(np.uint8)) if len(case["random_bg"]) else None
+    out = f.render_rays(float(case["t"]), o.cuda(), d.cuda(), white_bg=bool(g.cfg.dataset.white_background),
+                        ray_chunk=g.ray_chunk, jitter=torch.from_numpy(case["jitter"]), chunk_bg=bg)
+    lw = {k: v.cuda() for k, v in g.loss_weights().items()}
+    scalar_loss(out, lw).backward()
+    params = dict(f.named_parameters())
+    tol = TOL[mode]
+    errs = {}
+    for k, v in case.items():
+        if k.startswith("grad/vel_net.weight_net"):
+            name = k[len("grad/"):]
+            assert params[name].grad is not None, name
+            errs[name] = norm_rel_err(params[name].grad.cpu(), v)
+    if float(case["t"]) and errs:
+        bad = {k: v for k, v in errs.items() if not v < tol}
+        assert not bad, bad
+        assert len(errs) == 12
