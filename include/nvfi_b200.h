@@ -318,6 +318,10 @@ int nvfi_debug_mma_mn(const float* At, const float* G, float* Dout, uint32_t lbo
                       uint32_t sbo_field, uint32_t kstep_bytes, uint32_t layout_type,
                       uint32_t b_mn_major, void* stream);
 
+/* Development aid: (tag, clock64) pairs recorded by CTA 0 of the tensor-core backward at its phase
+ * boundaries into dev_buf (cap int64 entries); NULL disables. */
+int nvfi_debug_timeline(long long* dev_buf, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,6 +128,7 @@ SIGNATURES = {
     "nvfi_app_feature": (_i, [C.POINTER(NvfiField), _vp, _i64, _vp, _vp, _vp]),
     "nvfi_velocity": (_i, [C.POINTER(NvfiField), _vp, _i64, _i, _vp, _vp, _vp]),
     "nvfi_debug_mma_mn": (_i, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
+    "nvfi_debug_timeline": (_i, [_vp, _i]),
     "nvfi_pde_loss": (_i, [C.POINTER(NvfiField), _vp, _vp, _i64, _vp, C.POINTER(NvfiPdeGrads), _i, _vp, _vp]),
 }
 

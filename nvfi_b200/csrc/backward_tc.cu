@@ -33,16 +33,14 @@ constexpr int NT = tc::kThreads;            // 512 worker threads (+ the issuer 
 constexpr uint32_t kBwdStages = 2;          // ring depth: shared memory is needed for G
 constexpr int kLayerF = NVFI_TM * NVFI_TM;  // 16384 floats
 
-// per-CTA global workspace (float offsets)
-constexpr int TW_DW1 = 0;                       // dW^T of layers 1..4: [k][n], 4 x 16384
-constexpr int TW_DW0 = 4 * kLayerF;             // layer 0: [k < 32][n]
-constexpr int TW_HEAD = TW_DW0 + 32 * NVFI_TM;  // head: [k][8]
-constexpr int TW_B = TW_HEAD + NVFI_TM * 8;     // biases [6][128]
-constexpr int TW_PART_F = TW_B + 6 * NVFI_TM;   // floats to zero / reduce
-constexpr int TW_STASH = TW_PART_F;             // [2 evals][5 layers][m][n]
-constexpr int TW_XSTEPS = TW_STASH + 10 * kLayerF;
-constexpr int TW_GBUF = TW_XSTEPS + MAX_RK2_STEPS * 3 * NVFI_TM;   // [2][m][n] copies of G_l
-constexpr int TW_TOTAL = TW_GBUF + 2 * kLayerF;
+// Per-CTA global scratch (float offsets).  It is sized to stay L2-resident on all 148 SMs
+// (148 x 0.5 MB): one stash (the first evaluation of a step is recomputed after the second one
+// has been back-propagated, instead of keeping two stashes), two copies of G, the step positions.
+// Weight and bias gradients go straight to the packed gradient buffers with red.global.add.
+constexpr int TW_STASH = 0;                     // [5 layers][m][n]
+constexpr int TW_GBUF = TW_STASH + 5 * kLayerF + 32 * NVFI_TM; // (+ enc[m][32]); [2][m][n] copies of G_l
+constexpr int TW_XSTEPS = TW_GBUF + 2 * kLayerF;
+constexpr int TW_TOTAL = TW_XSTEPS + MAX_RK2_STEPS * 3 * NVFI_TM;
 
 struct BwdTile {
   float x0[3][NVFI_TM];
@@ -61,11 +59,31 @@ struct BwdTile {
   int batch;
 };
 
+// Development aid: when a buffer is registered with nvfi_debug_timeline, thread 0 of CTA 0
+// records (tag, clock64) pairs at the phase boundaries below (tools/probe_timeline.py).
+__device__ long long* g_tl_buf = nullptr;
+__device__ int g_tl_cap = 0;
+__device__ int g_tl_n = 0;
+__device__ __forceinline__ void TL(int tag) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && g_tl_buf != nullptr) {
+    const int i = g_tl_n;
+    if (i + 2 <= g_tl_cap) {
+      g_tl_buf[i] = tag;
+      g_tl_buf[i + 1] = clock64();
+      g_tl_n = i + 2;
+    }
+  }
+}
+
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void red_add(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
 }
 __device__ __forceinline__ float silu_d(float h) {   // SiLU'(h)
   const float s = 1.f / (1.f + __expf(-h));
@@ -175,9 +193,9 @@ __device__ __forceinline__ void issue_dw(tc::Ctl& c, tc::Issuer& is, uint32_t gt
 // and tval = its input.  Out: T.gout[0..2][m] = dL/d(x, y, z) through the network input; weight
 // and bias gradients added to the CTA's partials in `ws`.  Whole CTA (11 block barriers).
 __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned char* gt_hi,
-                            unsigned char* gt_lo, float* __restrict__ ws, const float* stash,
-                            const float* xs, const float* ys, const float* zs, float tval,
-                            uint32_t& dphase, int mode3) {
+                            unsigned char* gt_lo, float* __restrict__ ws, const NvfiRenderGrads& D,
+                            const float* stash, const float* xs, const float* ys, const float* zs,
+                            float tval, uint32_t& dphase, int mode3) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == tc::kIssuerWarp) {
     const uint32_t gh = tc::uniform(tc::smem_u32(gt_hi)), gl = tc::uniform(tc::smem_u32(gt_lo));
@@ -201,6 +219,7 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
   float* gbuf = ws + TW_GBUF;
 
+  TL(100);
   // ---- head layer (128 -> 6), FP32 SIMT: G_4 -> TMEM + global copy; dW5, db5
   {
     float gw[6];
@@ -235,16 +254,17 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
       for (int n = 0; n < 6; ++n) acc[n] = fmaf(a, T.gout[n][mm], acc[n]);
     }
 #pragma unroll
-    for (int n = 0; n < 6; ++n) red_add(ws + TW_HEAD + k * 8 + n, acc[n]);
-    if (tid < 6) {
-      float s = 0.f;
-      for (int mm = 0; mm < NVFI_TM; ++mm) s += T.gout[tid][mm];
-      red_add(ws + TW_B + 5 * NVFI_TM + tid, s);
+    for (int n = 0; n < 6; ++n) red_add(D.g_vel_w[5] + k * 8 + n, acc[n]);
+    if (warp < 6) {   // db5[n] = sum_m gout[n][m]: one warp per output
+      float s = T.gout[warp][lane] + T.gout[warp][lane + 32] + T.gout[warp][lane + 64] + T.gout[warp][lane + 96];
+      s = warp_sum(s);
+      if (lane == 0) red_add(D.g_vel_b[5] + warp, s);
     }
     tc::tmem_st_wait();
   }
   tc::tc_fence_before();
   __syncthreads();   // (A)
+  TL(101);
 
 #pragma unroll 1
   for (int l = 4; l >= 0; --l) {
@@ -261,12 +281,14 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
         s += v[i];
       }
       op_store_row32(gt_hi, gt_lo, k, h, v, mode3);
-      red_add(ws + TW_B + l * NVFI_TM + k, s);
+      red_add(D.g_vel_b[l] + k, s);
       fence_async_smem();
     }
+    TL(110 + l);
     tc::mbar_wait(&c.dbar, dphase & 1);   // dX accumulator
     ++dphase;
     tc::tc_fence_after();
+    TL(120 + l);
     // ---- dX epilogue (sample-major): G_{l-1} in registers, global copy; or the encoder chain rule
     float gnew[32];
     if (l > 0) {
@@ -289,14 +311,15 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         float s1, c1, s2, c2, s4, c4;
-        sincosf(qv[i], &s1, &c1);
-        sincosf(qv[i] * 2.f, &s2, &c2);
-        sincosf(qv[i] * 4.f, &s4, &c4);
+        tc::sincos_bounded(qv[i], s1, c1);
+        tc::sincos_bounded(qv[i] * 2.f, s2, c2);
+        tc::sincos_bounded(qv[i] * 4.f, s4, c4);
         T.gout[i][m] = gnew[i] + gnew[4 + i] * c1 - gnew[8 + i] * s1 +
                        2.f * (gnew[12 + i] * c2 - gnew[16 + i] * s2) +
                        4.f * (gnew[20 + i] * c4 - gnew[24 + i] * s4);
       }
     }
+    TL(130 + l);
     // ---- A_{l-1}^T into the TMEM operand region (the dX MMAs have finished reading G_l there)
     {
       float v[32];
@@ -305,52 +328,39 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = silu_v(__ldcg(sp + (size_t)(h * 32 + i) * NVFI_TM));
       } else {
-        // encoding^T (models/base_network.py:42-54): unit k < 28 of samples [32 h, +32)
-        const int grp = k >> 2, ci = k & 3;
+        // encoding^T from the copy the forward recompute stashed: unit k < 32 of samples [32 h, +32)
+        const float* ep = stash + (size_t)5 * kLayerF + k;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int mm = h * 32 + i;
-          const float qv = (ci == 0) ? xs[mm] : (ci == 1) ? ys[mm] : (ci == 2) ? zs[mm] : tval;
-          float r = 0.f;
-          if (k < 28) {
-            const float f = (grp <= 2) ? 1.f : ((grp <= 4) ? 2.f : 4.f);
-            if (grp == 0) r = qv;
-            else if (grp & 1) r = sinf(qv * f);
-            else r = cosf(qv * f);
-          }
-          v[i] = r;
-        }
+        for (int i = 0; i < 32; ++i) v[i] = (k < 32) ? __ldcg(ep + (size_t)(h * 32 + i) * 32) : 0.f;
       }
       tm_store32(tb, lane_base, h, v, mode3);
       tc::tmem_st_wait();
     }
+    TL(140 + l);
     tc::tc_fence_before();
     __syncthreads();   // (B)
+    TL(150 + l);
     tc::mbar_wait(&c.dbar, dphase & 1);   // dW accumulator
     ++dphase;
     tc::tc_fence_after();
+    TL(160 + l);
     // ---- dW^T flush (unit-major) and G_{l-1} into the TMEM operand region (sample-major)
     if (l > 0 || q == 0) {
       float dwv[32];
       tc::tmem_ld32(tb + lane_base + tc::kColD + 128u + (uint32_t)(h * 32), dwv);
-      float4* wp = reinterpret_cast<float4*>(ws + ((l > 0) ? (TW_DW1 + (l - 1) * kLayerF) : TW_DW0) +
-                                             k * NVFI_TM + h * 32);
+      float* wp = D.g_vel_w[l] + k * NVFI_TM + h * 32;   // packed W^T gradient: [k][n]
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 o = wp[j];
-        o.x += dwv[4 * j + 0];
-        o.y += dwv[4 * j + 1];
-        o.z += dwv[4 * j + 2];
-        o.w += dwv[4 * j + 3];
-        wp[j] = o;
-      }
+      for (int j = 0; j < 8; ++j)
+        red_add4(wp + 4 * j, dwv[4 * j + 0], dwv[4 * j + 1], dwv[4 * j + 2], dwv[4 * j + 3]);
     }
     if (l > 0) {
       tm_store32(tb, lane_base, h, gnew, mode3);
       tc::tmem_st_wait();
     }
+    TL(170 + l);
     tc::tc_fence_before();
     __syncthreads();   // (C)
+    TL(180 + l);
   }
 }
 
@@ -409,10 +419,11 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
       ctl.prog[n++] = tc::SEG_FWD0;
       ctl.prog[n++] = tc::SEG_FWD0;
     }
-    for (int k = 0; k < n_steps; ++k) {
+    for (int k = 0; k < n_steps; ++k) {   // F1, F2 (stash), B2, F1 again (stash), B1
       ctl.prog[n++] = tc::SEG_FWD0;
       ctl.prog[n++] = tc::SEG_FWD0;
       ctl.prog[n++] = tc::SEG_BWD0;
+      ctl.prog[n++] = tc::SEG_FWD0;
       ctl.prog[n++] = tc::SEG_BWD0;
     }
     ctl.prog_len = (uint32_t)n;
@@ -421,7 +432,6 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
     const int n = i / NVFI_TM, kk = i - n * NVFI_TM;
     T.w5s[n][kk] = __ldg(F.vel_net[5].wt + (size_t)kk * F.vel_net[5].n_pad + n);
   }
-  for (int i = tid; i < TW_PART_F; i += blockDim.x) ws[i] = 0.f;
   __syncthreads();
   tc::Issuer is;
   is.init(ctl, tc::smem_u32(ring), kBwdStages);
@@ -432,16 +442,14 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
   bool exhausted = false;
   int qc = 0, par = 0;
   unsigned long long n_done = 0;
-  float* stash0 = ws + TW_STASH;
-  float* stash1 = ws + TW_STASH + 5 * kLayerF;
+  float* stash = ws + TW_STASH;
   float* xsteps = ws + TW_XSTEPS;
 
-  auto net_fwd = [&](float* wout, const float* xs, const float* ys, const float* zs, float* stash) {
-    if (stash)
-      tc::vel_net_tile_tc<ACT_SILU, true>(ctl, is, 0, wout, xs, ys, zs, T.tvec, dphase, kphase, mode3, stash);
-    else
-      tc::vel_net_tile_tc<ACT_SILU, false>(ctl, is, 0, wout, xs, ys, zs, T.tvec, dphase, kphase, mode3);
-  };
+  // One tile = a short program of evaluations.  There is exactly ONE call site of the forward
+  // tile evaluation and one of the backward tile evaluation (the kernel would not fit the
+  // instruction cache otherwise); the small per-sample glue around them is selected by `kind`.
+  enum { K_FWD_A = 0, K_FWD_B, K_REV_A, K_REV_B, K_BWD2, K_REV_C, K_BWD1 };
+  const int n_ops = 2 * (n_steps - 1) + 5 * n_steps;
 
   for (;;) {
     while (qc < NVFI_TM && !exhausted) {
@@ -477,6 +485,7 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
     }
     if (qc == 0) break;
     __syncthreads();
+    TL(0);
     const int n = min(NVFI_TM, qc);
     const int start = qc - n;
     qc = start;
@@ -507,141 +516,114 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
       }
     }
     __syncthreads();
-    // ---- forward sweep over all but the last step, remembering the step start positions
-    for (int k = 0; k + 1 < n_steps; ++k) {
-      const float dt = sched_dt[k], tcur = sched_t[k], hdt = 0.5f * dt;
-      if (tid < NVFI_TM) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) xsteps[(k * 3 + a) * NVFI_TM + tid] = T.x0[a][tid];
-        T.tvec[tid] = tcur;
+
+#pragma unroll 1
+    for (int op = 0; op < n_ops; ++op) {
+      int k, kind;
+      if (op < 2 * (n_steps - 1)) {   // forward sweep over all but the last step
+        k = op >> 1;
+        kind = K_FWD_A + (op & 1);
+      } else {                        // reverse sweep
+        const int r = op - 2 * (n_steps - 1);
+        k = n_steps - 1 - r / 5;
+        kind = K_REV_A + r % 5;
       }
-      __syncthreads();
-      net_fwd(&T.w0[0][0], T.x0[0], T.x0[1], T.x0[2], nullptr);
-      if (tid < NVFI_TM) {
-        const int m = tid;
-        const float x = T.x0[0][m], y = T.x0[1][m], z = T.x0[2][m];
-        float v[3] = {0.f, 0.f, 0.f};
-        if (!gate_outside(F, x, y, z)) {
-          const float w[6] = {T.w0[0][m], T.w0[1][m], T.w0[2][m], T.w0[3][m], T.w0[4][m], T.w0[5][m]};
-          basis_velocity(w, x, y, z, v);
-        }
-        T.xm[0][m] = __fsub_rn(x, __fmul_rn(hdt, v[0]));
-        T.xm[1][m] = __fsub_rn(y, __fmul_rn(hdt, v[1]));
-        T.xm[2][m] = __fsub_rn(z, __fmul_rn(hdt, v[2]));
-        T.tvec[m] = __fsub_rn(tcur, hdt);
-      }
-      __syncthreads();
-      net_fwd(&T.w1[0][0], T.xm[0], T.xm[1], T.xm[2], nullptr);
-      if (tid < NVFI_TM) {
-        const int m = tid;
-        const float xm = T.xm[0][m], ym = T.xm[1][m], zm = T.xm[2][m];
-        float v[3] = {0.f, 0.f, 0.f};
-        if (!gate_outside(F, xm, ym, zm)) {
-          const float w[6] = {T.w1[0][m], T.w1[1][m], T.w1[2][m], T.w1[3][m], T.w1[4][m], T.w1[5][m]};
-          basis_velocity(w, xm, ym, zm, v);
-        }
-        const float x = T.x0[0][m], y = T.x0[1][m], z = T.x0[2][m];
-        float nx = __fsub_rn(x, __fmul_rn(dt, v[0]));
-        float ny = __fsub_rn(y, __fmul_rn(dt, v[1]));
-        float nz = __fsub_rn(z, __fmul_rn(dt, v[2]));
-        if (F.vel_gate == NVFI_GATE_SUR && gate_outside(F, nx, ny, nz)) {
-          nx = x;
-          ny = y;
-          nz = z;
-        }
-        T.x0[0][m] = nx;
-        T.x0[1][m] = ny;
-        T.x0[2][m] = nz;
-      }
-      __syncthreads();
-    }
-    // ---- reverse sweep
-    for (int k = n_steps - 1; k >= 0; --k) {
       const float dt = sched_dt[k], tcur = sched_t[k], hdt = 0.5f * dt;
       const float tmid = __fsub_rn(tcur, hdt);
+      // ---- glue before the evaluation
       if (tid < NVFI_TM) {
-        if (k < n_steps - 1) {
+        if (kind == K_FWD_A) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) xsteps[(k * 3 + a) * NVFI_TM + tid] = T.x0[a][tid];
+        }
+        if (kind == K_REV_A && k < n_steps - 1) {
 #pragma unroll
           for (int a = 0; a < 3; ++a) T.x0[a][tid] = xsteps[(k * 3 + a) * NVFI_TM + tid];
         }
-        T.tvec[tid] = tcur;
+        if (kind == K_FWD_A || kind == K_REV_A || kind == K_REV_C) T.tvec[tid] = tcur;
+        if (kind == K_FWD_B || kind == K_REV_B) T.tvec[tid] = tmid;
       }
       __syncthreads();
-      net_fwd(&T.w0[0][0], T.x0[0], T.x0[1], T.x0[2], stash0);
+      const bool at_mid = (kind == K_FWD_B || kind == K_REV_B || kind == K_BWD2);
+      const float* xs = at_mid ? T.xm[0] : T.x0[0];
+      const float* ys = at_mid ? T.xm[1] : T.x0[1];
+      const float* zs = at_mid ? T.xm[2] : T.x0[2];
+      if (kind == K_BWD2 || kind == K_BWD1) {
+        bwd_eval_tc(ctl, is, T, g_hi, g_lo, ws, D, stash, xs, ys, zs, at_mid ? tmid : tcur, dphase, mode3);
+      } else {
+        TL(1);
+        float* wout = (kind == K_FWD_A || kind == K_REV_A) ? &T.w0[0][0] : &T.w1[0][0];
+        float* st = (kind == K_REV_B || kind == K_REV_C) ? stash : nullptr;
+        tc::vel_net_tile_tc<ACT_SILU>(ctl, is, 0, wout, xs, ys, zs, T.tvec, dphase, kphase, mode3, st);
+      }
+      // ---- glue after the evaluation
       if (tid < NVFI_TM) {
         const int m = tid;
-        const float x = T.x0[0][m], y = T.x0[1][m], z = T.x0[2][m];
-        float v[3] = {0.f, 0.f, 0.f};
-        const bool out0 = gate_outside(F, x, y, z);
-        T.gate0[m] = out0;
-        if (!out0) {
-          const float w[6] = {T.w0[0][m], T.w0[1][m], T.w0[2][m], T.w0[3][m], T.w0[4][m], T.w0[5][m]};
-          basis_velocity(w, x, y, z, v);
+        if (kind == K_FWD_A || kind == K_REV_A) {   // midpoint m = x0 - dt/2 v0(x0)
+          const float x = T.x0[0][m], y = T.x0[1][m], z = T.x0[2][m];
+          float v[3] = {0.f, 0.f, 0.f};
+          const bool out0 = gate_outside(F, x, y, z);
+          T.gate0[m] = out0;
+          if (!out0) {
+            const float w[6] = {T.w0[0][m], T.w0[1][m], T.w0[2][m], T.w0[3][m], T.w0[4][m], T.w0[5][m]};
+            basis_velocity(w, x, y, z, v);
+          }
+          T.xm[0][m] = __fsub_rn(x, __fmul_rn(hdt, v[0]));
+          T.xm[1][m] = __fsub_rn(y, __fmul_rn(hdt, v[1]));
+          T.xm[2][m] = __fsub_rn(z, __fmul_rn(hdt, v[2]));
+        } else if (kind == K_FWD_B || kind == K_REV_B) {   // x1 = x0 - dt v1(m)
+          const float xm = T.xm[0][m], ym = T.xm[1][m], zm = T.xm[2][m];
+          const bool out1 = gate_outside(F, xm, ym, zm);
+          const float w[6] = {T.w1[0][m], T.w1[1][m], T.w1[2][m], T.w1[3][m], T.w1[4][m], T.w1[5][m]};
+          float v[3] = {0.f, 0.f, 0.f};
+          if (!out1) basis_velocity(w, xm, ym, zm, v);
+          const float x = T.x0[0][m], y = T.x0[1][m], z = T.x0[2][m];
+          float nx = __fsub_rn(x, __fmul_rn(dt, v[0]));
+          float ny = __fsub_rn(y, __fmul_rn(dt, v[1]));
+          float nz = __fsub_rn(z, __fmul_rn(dt, v[2]));
+          const bool rev = (F.vel_gate == NVFI_GATE_SUR) && gate_outside(F, nx, ny, nz);
+          if (kind == K_FWD_B) {      // advance to the next step
+            T.x0[0][m] = rev ? x : nx;
+            T.x0[1][m] = rev ? y : ny;
+            T.x0[2][m] = rev ? z : nz;
+          } else {                    // adjoint of x1 = x0 - dt v1(m)
+            T.gate1[m] = out1;
+            T.reverted[m] = rev;
+            float gw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gxe[3] = {0.f, 0.f, 0.f};
+            if (!rev && !out1) {
+              const float gv[3] = {-dt * T.gbar[0][m], -dt * T.gbar[1][m], -dt * T.gbar[2][m]};
+              basis_bwd(w, xm, ym, zm, gv, gw, gxe);
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) T.gout[i][m] = gw[i];
+            T.gm[0][m] = gxe[0];
+            T.gm[1][m] = gxe[1];
+            T.gm[2][m] = gxe[2];
+          }
+        } else if (kind == K_BWD2) {   // adjoint of m = x0 - dt/2 v0(x0)
+          float gmv[3];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) gmv[a] = T.gm[a][m] + T.gout[a][m];
+          float gx0[3] = {T.gbar[0][m] + gmv[0], T.gbar[1][m] + gmv[1], T.gbar[2][m] + gmv[2]};
+          float gw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (!T.gate0[m]) {
+            const float w[6] = {T.w0[0][m], T.w0[1][m], T.w0[2][m], T.w0[3][m], T.w0[4][m], T.w0[5][m]};
+            const float gv[3] = {-hdt * gmv[0], -hdt * gmv[1], -hdt * gmv[2]};
+            float gxe[3];
+            basis_bwd(w, T.x0[0][m], T.x0[1][m], T.x0[2][m], gv, gw, gxe);
+            gx0[0] += gxe[0];
+            gx0[1] += gxe[1];
+            gx0[2] += gxe[2];
+          }
+          T.gbar[0][m] = gx0[0];
+          T.gbar[1][m] = gx0[1];
+          T.gbar[2][m] = gx0[2];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) T.gout[i][m] = gw[i];
+        } else if (kind == K_BWD1) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) T.gbar[a][m] += T.gout[a][m];
         }
-        T.xm[0][m] = __fsub_rn(x, __fmul_rn(hdt, v[0]));
-        T.xm[1][m] = __fsub_rn(y, __fmul_rn(hdt, v[1]));
-        T.xm[2][m] = __fsub_rn(z, __fmul_rn(hdt, v[2]));
-        T.tvec[m] = tmid;
-      }
-      __syncthreads();
-      net_fwd(&T.w1[0][0], T.xm[0], T.xm[1], T.xm[2], stash1);
-      // adjoint of x1 = x0 - dt v1(m)
-      if (tid < NVFI_TM) {
-        const int m = tid;
-        const float xm = T.xm[0][m], ym = T.xm[1][m], zm = T.xm[2][m];
-        const bool out1 = gate_outside(F, xm, ym, zm);
-        const float w[6] = {T.w1[0][m], T.w1[1][m], T.w1[2][m], T.w1[3][m], T.w1[4][m], T.w1[5][m]};
-        float v[3] = {0.f, 0.f, 0.f};
-        if (!out1) basis_velocity(w, xm, ym, zm, v);
-        const float x = T.x0[0][m], y = T.x0[1][m], z = T.x0[2][m];
-        const float nx = __fsub_rn(x, __fmul_rn(dt, v[0]));
-        const float ny = __fsub_rn(y, __fmul_rn(dt, v[1]));
-        const float nz = __fsub_rn(z, __fmul_rn(dt, v[2]));
-        const bool rev = (F.vel_gate == NVFI_GATE_SUR) && gate_outside(F, nx, ny, nz);
-        T.gate1[m] = out1;
-        T.reverted[m] = rev;
-        float gw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gxe[3] = {0.f, 0.f, 0.f};
-        if (!rev && !out1) {
-          const float gv[3] = {-dt * T.gbar[0][m], -dt * T.gbar[1][m], -dt * T.gbar[2][m]};
-          basis_bwd(w, xm, ym, zm, gv, gw, gxe);
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) T.gout[i][m] = gw[i];
-        T.gm[0][m] = gxe[0];
-        T.gm[1][m] = gxe[1];
-        T.gm[2][m] = gxe[2];
-      }
-      __syncthreads();
-      bwd_eval_tc(ctl, is, T, g_hi, g_lo, ws, stash1, T.xm[0], T.xm[1], T.xm[2], tmid, dphase, mode3);
-      // adjoint of m = x0 - dt/2 v0(x0)
-      if (tid < NVFI_TM) {
-        const int m = tid;
-        float gmv[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) gmv[a] = T.gm[a][m] + T.gout[a][m];
-        float gx0[3] = {T.gbar[0][m] + gmv[0], T.gbar[1][m] + gmv[1], T.gbar[2][m] + gmv[2]};
-        float gw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (!T.gate0[m]) {
-          const float w[6] = {T.w0[0][m], T.w0[1][m], T.w0[2][m], T.w0[3][m], T.w0[4][m], T.w0[5][m]};
-          const float gv[3] = {-hdt * gmv[0], -hdt * gmv[1], -hdt * gmv[2]};
-          float gxe[3];
-          basis_bwd(w, T.x0[0][m], T.x0[1][m], T.x0[2][m], gv, gw, gxe);
-          gx0[0] += gxe[0];
-          gx0[1] += gxe[1];
-          gx0[2] += gxe[2];
-        }
-        T.gbar[0][m] = gx0[0];
-        T.gbar[1][m] = gx0[1];
-        T.gbar[2][m] = gx0[2];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) T.gout[i][m] = gw[i];
-      }
-      __syncthreads();
-      bwd_eval_tc(ctl, is, T, g_hi, g_lo, ws, stash0, T.x0[0], T.x0[1], T.x0[2], tcur, dphase, mode3);
-      if (tid < NVFI_TM) {
-        const int m = tid;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) T.gbar[a][m] += T.gout[a][m];
       }
       __syncthreads();
     }
@@ -651,22 +633,20 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
     atomicAdd(reinterpret_cast<unsigned long long*>(B.counters + 10), n_done);
 }
 
-// g[e] += sum over CTAs of ws[c][off + e]
-__global__ void k_reduce_plain(const float* __restrict__ ws, int n_cta, int off, int n,
-                               float* __restrict__ g) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
-  float s = 0.f;
-  for (int c = 0; c < n_cta; ++c) s += ws[(size_t)c * WS_CTA_F + off + e];
-  g[e] += s;
-}
-
 }  // namespace tcb
 }  // namespace nvfi
 
 using namespace nvfi;
 
 static_assert(tcb::TW_TOTAL <= WS_CTA_F, "per-CTA workspace of the tensor-core backward exceeds WS_CTA_F");
+
+extern "C" int nvfi_debug_timeline(long long* dev_buf, int cap) {
+  const int zero = 0;
+  NVFI_CUDA_OK(cudaMemcpyToSymbol(tcb::g_tl_buf, &dev_buf, sizeof(dev_buf)));
+  NVFI_CUDA_OK(cudaMemcpyToSymbol(tcb::g_tl_cap, &cap, sizeof(cap)));
+  NVFI_CUDA_OK(cudaMemcpyToSymbol(tcb::g_tl_n, &zero, sizeof(zero)));
+  return NVFI_OK;
+}
 
 extern "C" int nvfi_launch_advect_bwd_tc(const NvfiField* F, const NvfiRenderArgs* A,
                                          const NvfiRenderBuffers* B, const NvfiRenderGrads* D, int S,
@@ -689,17 +669,5 @@ extern "C" int nvfi_launch_advect_bwd_tc(const NvfiField* F, const NvfiRenderArg
   const int n_batches = (int)((total + per_batch - 1) / per_batch);
   const int grid = n_batches < sms ? n_batches : sms;
   NVFI_LAUNCH(tcb::k_advect_bwd_tc, grid, tc::kLaunchThreads, smem, st, *F, *A, *B, *D, S, total, n_batches, mode);
-  NVFI_CUDA_OK(cudaGetLastError());
-  for (int l = 1; l <= 4; ++l)
-    NVFI_LAUNCH(tcb::k_reduce_plain, tcb::kLayerF / 256, 256, 0, st, D->workspace, grid,
-                tcb::TW_DW1 + (l - 1) * tcb::kLayerF, tcb::kLayerF, D->g_vel_w[l]);
-  NVFI_LAUNCH(tcb::k_reduce_plain, 32 * NVFI_TM / 256, 256, 0, st, D->workspace, grid, tcb::TW_DW0,
-              32 * NVFI_TM, D->g_vel_w[0]);
-  NVFI_LAUNCH(tcb::k_reduce_plain, NVFI_TM * 8 / 256, 256, 0, st, D->workspace, grid, tcb::TW_HEAD,
-              NVFI_TM * 8, D->g_vel_w[5]);
-  for (int l = 0; l < 5; ++l)
-    NVFI_LAUNCH(tcb::k_reduce_plain, 1, 128, 0, st, D->workspace, grid, tcb::TW_B + l * NVFI_TM, NVFI_TM,
-                D->g_vel_b[l]);
-  NVFI_LAUNCH(tcb::k_reduce_plain, 1, 128, 0, st, D->workspace, grid, tcb::TW_B + 5 * NVFI_TM, 8, D->g_vel_b[5]);
   return (int)cudaGetLastError();
 }
