@@ -33,12 +33,12 @@ constexpr int NT = tc::kThreads;            // 512 worker threads (+ the issuer 
 constexpr uint32_t kBwdStages = 2;          // ring depth: shared memory is needed for G
 constexpr int kLayerF = NVFI_TM * NVFI_TM;  // 16384 floats
 
-// Per-CTA global scratch (float offsets).  It is sized to stay L2-resident on all 148 SMs
-// (148 x 0.5 MB): one stash (the first evaluation of a step is recomputed after the second one
-// has been back-propagated, instead of keeping two stashes), two copies of G, the step positions.
-// Weight and bias gradients go straight to the packed gradient buffers with red.global.add.
-constexpr int TW_STASH = 0;                     // [5 layers][m][n]
-constexpr int TW_GBUF = TW_STASH + 5 * kLayerF + 32 * NVFI_TM; // (+ enc[m][32]); [2][m][n] copies of G_l
+// Per-CTA global scratch (float offsets): the stashes of the two evaluations of a step, two
+// copies of G, the step positions.  Weight and bias gradients go straight to the packed
+// gradient buffers with red.global.add (no per-CTA partials, no reduce kernels).
+constexpr int kStashF = 5 * kLayerF + 32 * NVFI_TM;   // [5 layers][m][n] + enc[m][32]
+constexpr int TW_STASH = 0;                     // [2 evals][kStashF]
+constexpr int TW_GBUF = TW_STASH + 2 * kStashF; // [2][m][n] copies of G_l
 constexpr int TW_XSTEPS = TW_GBUF + 2 * kLayerF;
 constexpr int TW_TOTAL = TW_XSTEPS + MAX_RK2_STEPS * 3 * NVFI_TM;
 
@@ -85,11 +85,17 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
 }
-__device__ __forceinline__ float silu_d(float h) {   // SiLU'(h)
-  const float s = 1.f / (1.f + __expf(-h));
-  return s * (1.f + h * (1.f - s));
+__device__ __forceinline__ float sigmoid_fast(float h) {   // ex2.approx + rcp.approx, no fix-up code
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(h * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
 }
-__device__ __forceinline__ float silu_v(float h) { return h / (1.f + __expf(-h)); }
+__device__ __forceinline__ float silu_d(float h) {   // SiLU'(h) = s + h s (1 - s)
+  const float s = sigmoid_fast(h);
+  return fmaf(h * s, 1.f - s, s);
+}
+__device__ __forceinline__ float silu_v(float h) { return h * sigmoid_fast(h); }
 
 // Thread (row r, 32-wide K block h): write 32 values of row r, columns [32 h, +32) of a
 // 128 x 128 FP32 operand tile, split hi/lo.  Layout: four K blocks of 16 KB, rows of 128 bytes,
@@ -195,7 +201,8 @@ __device__ __forceinline__ void issue_dw(tc::Ctl& c, tc::Issuer& is, uint32_t gt
 __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned char* gt_hi,
                             unsigned char* gt_lo, float* __restrict__ ws, const NvfiRenderGrads& D,
                             const float* stash, const float* xs, const float* ys, const float* zs,
-                            float tval, uint32_t& dphase, int mode3) {
+                            float tval, uint32_t& dphase, int mode3, float (&acc_head)[6],
+                            float (&acc_bias)[6]) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == tc::kIssuerWarp) {
     const uint32_t gh = tc::uniform(tc::smem_u32(gt_hi)), gl = tc::uniform(tc::smem_u32(gt_lo));
@@ -254,12 +261,9 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
       for (int n = 0; n < 6; ++n) acc[n] = fmaf(a, T.gout[n][mm], acc[n]);
     }
 #pragma unroll
-    for (int n = 0; n < 6; ++n) red_add(D.g_vel_w[5] + k * 8 + n, acc[n]);
-    if (warp < 6) {   // db5[n] = sum_m gout[n][m]: one warp per output
-      float s = T.gout[warp][lane] + T.gout[warp][lane + 32] + T.gout[warp][lane + 64] + T.gout[warp][lane + 96];
-      s = warp_sum(s);
-      if (lane == 0) red_add(D.g_vel_b[5] + warp, s);
-    }
+    for (int n = 0; n < 6; ++n) acc_head[n] += acc[n];   // flushed once, at kernel end
+    if (warp < 6)     // db5[n] = sum_m gout[n][m]: warp n, each lane 4 samples (reduced at kernel end)
+      acc_bias[5] += T.gout[warp][lane] + T.gout[warp][lane + 32] + T.gout[warp][lane + 64] + T.gout[warp][lane + 96];
     tc::tmem_st_wait();
   }
   tc::tc_fence_before();
@@ -281,7 +285,7 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
         s += v[i];
       }
       op_store_row32(gt_hi, gt_lo, k, h, v, mode3);
-      red_add(D.g_vel_b[l] + k, s);
+      acc_bias[l] += s;   // unit k, samples [32 h, +32): flushed once, at kernel end
       fence_async_smem();
     }
     TL(110 + l);
@@ -329,7 +333,7 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
         for (int i = 0; i < 32; ++i) v[i] = silu_v(__ldcg(sp + (size_t)(h * 32 + i) * NVFI_TM));
       } else {
         // encoding^T from the copy the forward recompute stashed: unit k < 32 of samples [32 h, +32)
-        const float* ep = stash + (size_t)5 * kLayerF + k;
+        const float* ep = stash + (size_t)5 * kLayerF + k;   // enc[m][32] follows the 5 layers
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = (k < 32) ? __ldcg(ep + (size_t)(h * 32 + i) * 32) : 0.f;
       }
@@ -378,6 +382,8 @@ __device__ __forceinline__ void basis_bwd(const float w[6], float x, float y, fl
   gxe[2] = -w[4] * gv[0] + w[3] * gv[1];
 }
 
+// 17 warps are allocated as 20 (groups of 4 per scheduler): 96 registers per thread is the cap
+// (a 112-register build fails to launch).
 __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
     k_advect_bwd_tc(const __grid_constant__ NvfiField F, const NvfiRenderArgs A, const NvfiRenderBuffers B,
                     const NvfiRenderGrads D, int S, long long total, int n_batches, int mode) {
@@ -419,11 +425,10 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
       ctl.prog[n++] = tc::SEG_FWD0;
       ctl.prog[n++] = tc::SEG_FWD0;
     }
-    for (int k = 0; k < n_steps; ++k) {   // F1, F2 (stash), B2, F1 again (stash), B1
+    for (int k = 0; k < n_steps; ++k) {   // F1, F2 (both stashed), B2, B1
       ctl.prog[n++] = tc::SEG_FWD0;
       ctl.prog[n++] = tc::SEG_FWD0;
       ctl.prog[n++] = tc::SEG_BWD0;
-      ctl.prog[n++] = tc::SEG_FWD0;
       ctl.prog[n++] = tc::SEG_BWD0;
     }
     ctl.prog_len = (uint32_t)n;
@@ -444,12 +449,15 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
   unsigned long long n_done = 0;
   float* stash = ws + TW_STASH;
   float* xsteps = ws + TW_XSTEPS;
+  // per-thread partial sums of the head-layer weight gradient (unit k = tid & 127) and of the
+  // bias gradients, carried in registers across all tiles of this CTA
+  float acc_head[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, acc_bias[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
   // One tile = a short program of evaluations.  There is exactly ONE call site of the forward
   // tile evaluation and one of the backward tile evaluation (the kernel would not fit the
   // instruction cache otherwise); the small per-sample glue around them is selected by `kind`.
-  enum { K_FWD_A = 0, K_FWD_B, K_REV_A, K_REV_B, K_BWD2, K_REV_C, K_BWD1 };
-  const int n_ops = 2 * (n_steps - 1) + 5 * n_steps;
+  enum { K_FWD_A = 0, K_FWD_B, K_REV_A, K_REV_B, K_BWD2, K_BWD1 };
+  const int n_ops = 2 * (n_steps - 1) + 4 * n_steps;
 
   for (;;) {
     while (qc < NVFI_TM && !exhausted) {
@@ -525,8 +533,8 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
         kind = K_FWD_A + (op & 1);
       } else {                        // reverse sweep
         const int r = op - 2 * (n_steps - 1);
-        k = n_steps - 1 - r / 5;
-        kind = K_REV_A + r % 5;
+        k = n_steps - 1 - (r >> 2);
+        kind = K_REV_A + (r & 3);
       }
       const float dt = sched_dt[k], tcur = sched_t[k], hdt = 0.5f * dt;
       const float tmid = __fsub_rn(tcur, hdt);
@@ -540,7 +548,7 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
 #pragma unroll
           for (int a = 0; a < 3; ++a) T.x0[a][tid] = xsteps[(k * 3 + a) * NVFI_TM + tid];
         }
-        if (kind == K_FWD_A || kind == K_REV_A || kind == K_REV_C) T.tvec[tid] = tcur;
+        if (kind == K_FWD_A || kind == K_REV_A) T.tvec[tid] = tcur;
         if (kind == K_FWD_B || kind == K_REV_B) T.tvec[tid] = tmid;
       }
       __syncthreads();
@@ -549,11 +557,12 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
       const float* ys = at_mid ? T.xm[1] : T.x0[1];
       const float* zs = at_mid ? T.xm[2] : T.x0[2];
       if (kind == K_BWD2 || kind == K_BWD1) {
-        bwd_eval_tc(ctl, is, T, g_hi, g_lo, ws, D, stash, xs, ys, zs, at_mid ? tmid : tcur, dphase, mode3);
+        bwd_eval_tc(ctl, is, T, g_hi, g_lo, ws, D, at_mid ? stash + kStashF : stash, xs, ys, zs,
+                    at_mid ? tmid : tcur, dphase, mode3, acc_head, acc_bias);
       } else {
         TL(1);
         float* wout = (kind == K_FWD_A || kind == K_REV_A) ? &T.w0[0][0] : &T.w1[0][0];
-        float* st = (kind == K_REV_B || kind == K_REV_C) ? stash : nullptr;
+        float* st = (kind == K_REV_A) ? stash : ((kind == K_REV_B) ? stash + kStashF : nullptr);
         tc::vel_net_tile_tc<ACT_SILU>(ctl, is, 0, wout, xs, ys, zs, T.tvec, dphase, kphase, mode3, st);
       }
       // ---- glue after the evaluation
@@ -626,6 +635,17 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
         }
       }
       __syncthreads();
+    }
+  }
+  if (tid < NT) {
+    const int kk = tid & 127;
+#pragma unroll
+    for (int n2 = 0; n2 < 6; ++n2) red_add(D.g_vel_w[5] + kk * 8 + n2, acc_head[n2]);
+#pragma unroll
+    for (int l = 0; l < 5; ++l) red_add(D.g_vel_b[l] + kk, acc_bias[l]);
+    if (warp < 6) {
+      const float s5 = warp_sum(acc_bias[5]);
+      if (lane == 0) red_add(D.g_vel_b[5] + warp, s5);
     }
   }
   tc::teardown(ctl, is);

@@ -34,6 +34,8 @@ static cudaEvent_t get_event() {
 }
 
 ProfScope::ProfScope(const char* name, cudaStream_t st) : st_(st), idx_(-1) {
+  for (const char* p = name; *p; ++p)   // drop namespace qualifiers: "tcb::k_x" -> "k_x"
+    if (p[0] == ':' && p[1] == ':') name = p + 2;
   std::lock_guard<std::mutex> lk(g_mu);
   ++g_launches;
   if (!g_enabled) return;
