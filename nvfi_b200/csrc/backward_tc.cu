@@ -75,6 +75,15 @@ __device__ __forceinline__ void TL(int tag) {
   }
 }
 
+// ld.global.cg as a volatile asm: consecutive calls are issued back to back (the compiler may not
+// sink one below the use of another, which it otherwise does under register pressure and turns
+// eight independent L2 round trips into a serial chain).
+__device__ __forceinline__ float4 ldcg4_now(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -235,16 +244,21 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
     const float4* hp = reinterpret_cast<const float4*>(stash + ((size_t)4 * NVFI_TM + m) * NVFI_TM + h * 32);
     float v[32];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 hv = __ldcg(hp + j);
-      const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+    for (int half = 0; half < 2; ++half) {
+      float4 hv[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int kk = h * 32 + j * 4 + i;
-        float s = 0.f;
+      for (int j = 0; j < 4; ++j) hv[j] = ldcg4_now(hp + half * 4 + j);
 #pragma unroll
-        for (int n = 0; n < 6; ++n) s = fmaf(gw[n], T.w5s[n][kk], s);
-        v[j * 4 + i] = s * silu_d(hh[i]);
+      for (int j = 0; j < 4; ++j) {
+        const float hh[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int kk = h * 32 + half * 16 + j * 4 + i;
+          float s = 0.f;
+#pragma unroll
+          for (int n = 0; n < 6; ++n) s = fmaf(gw[n], T.w5s[n][kk], s);
+          v[half * 16 + j * 4 + i] = s * silu_d(hh[i]);
+        }
       }
     }
     tm_store32(tb, lane_base, h, v, mode3);
@@ -296,17 +310,24 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
     // ---- dX epilogue (sample-major): G_{l-1} in registers, global copy; or the encoder chain rule
     float gnew[32];
     if (l > 0) {
-      tc::tmem_ld32(tb + lane_base + tc::kColD + (uint32_t)(h * 32), gnew);
       const float4* hp = reinterpret_cast<const float4*>(stash + ((size_t)(l - 1) * NVFI_TM + m) * NVFI_TM + h * 32);
       float4* gp = reinterpret_cast<float4*>(gdst + (size_t)m * NVFI_TM + h * 32);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 hv = __ldcg(hp + j);
-        gnew[4 * j + 0] *= silu_d(hv.x);
-        gnew[4 * j + 1] *= silu_d(hv.y);
-        gnew[4 * j + 2] *= silu_d(hv.z);
-        gnew[4 * j + 3] *= silu_d(hv.w);
-        __stcg(gp + j, make_float4(gnew[4 * j], gnew[4 * j + 1], gnew[4 * j + 2], gnew[4 * j + 3]));
+      for (int half = 0; half < 2; ++half) {     // 16 columns at a time: 4 loads in flight, 48 live registers
+        float4 hv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hv[j] = ldcg4_now(hp + half * 4 + j);
+        float part[16];
+        tc::tmem_ld16(tb + lane_base + tc::kColD + (uint32_t)(h * 32 + half * 16), part);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int b = half * 16 + 4 * j;
+          gnew[b + 0] = part[4 * j + 0] * silu_d(hv[j].x);
+          gnew[b + 1] = part[4 * j + 1] * silu_d(hv[j].y);
+          gnew[b + 2] = part[4 * j + 2] * silu_d(hv[j].z);
+          gnew[b + 3] = part[4 * j + 3] * silu_d(hv[j].w);
+          __stcg(gp + half * 4 + j, make_float4(gnew[b], gnew[b + 1], gnew[b + 2], gnew[b + 3]));
+        }
       }
     } else if (h == 0) {
       // dL/d(encoding) -> dL/d(x, y, z)  (encoder tangents)

@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(128, 1)
     const uint32_t desc_hi = sbo_field | (1u << 14) | (layout_type << 29);
     const uint32_t gb = tc::smem_u32(g);
     for (uint32_t ks = 0; ks < 16; ++ks) {
-      const uint32_t lo = (((gb + ks * kstep_bytes) >> 4) & 0x3FFFu) | (lbo_field << 16);
+      // K step ks: 32-wide K block (ks >> 2) is 16 KB further, step (ks & 3) kstep_bytes further
+      // (kstep_bytes >= 1024 means: linear stepping, used by the MN-major variants)
+      const uint32_t adv = (kstep_bytes >= 1024u) ? ks * kstep_bytes : (ks >> 2) * 16384u + (ks & 3u) * kstep_bytes;
+      const uint32_t lo = (((gb + adv) >> 4) & 0x3FFFu) | (lbo_field << 16);
       const uint64_t bd = ((uint64_t)desc_hi << 32) | lo;
       tc::mma_tf32_ts(tb, tb + 128u + ks * 8u, bd, idesc, ks ? 1u : 0u);
     }
