@@ -203,10 +203,86 @@ __device__ __forceinline__ void issue_dw(tc::Ctl& c, tc::Issuer& is, uint32_t gt
   __syncwarp();
 }
 
+// Thread (sample m = 32 q + lane, unit block h): 32 values G[m][32 h + i] -> column m of rows
+// 32 h + i of the K-major G^T operand tile (K = sample), split hi/lo.  A warp writes one 128-byte
+// row segment per store (32 consecutive samples of one unit): conflict-free, and the transpose
+// costs no memory round trip.
+__device__ __forceinline__ void gt_store_col32(unsigned char* t_hi, unsigned char* t_lo, int q, int lane,
+                                               int h, const float v[32], int mode3) {
+  const uint32_t base = (uint32_t)((q << 14) + (h << 12) + ((lane & 3) << 2));
+  const uint32_t lc = (uint32_t)(lane >> 2);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const uint32_t off = base + (uint32_t)(((i >> 3) << 10) + ((i & 7) << 7)) + ((lc ^ (uint32_t)(i & 7)) << 4);
+    const float hi = __uint_as_float(tc::to_tf32(v[i]));
+    *reinterpret_cast<float*>(t_hi + off) = hi;
+    if (mode3) *reinterpret_cast<float*>(t_lo + off) = v[i] - hi;
+  }
+}
+
+// Thread (unit k, sample block h): sum over the 32 samples of block h of row k of the G^T tile.
+__device__ __forceinline__ float gt_row_sum(const unsigned char* t_hi, const unsigned char* t_lo, int k, int h,
+                                            int mode3) {
+  const uint32_t row = (uint32_t)((h << 14) + ((k >> 3) << 10) + ((k & 7) << 7));
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 a = *reinterpret_cast<const float4*>(t_hi + row + (j << 4));
+    s0 += (a.x + a.y) + (a.z + a.w);
+    if (mode3) {
+      const float4 b = *reinterpret_cast<const float4*>(t_lo + row + (j << 4));
+      s1 += (b.x + b.y) + (b.z + b.w);
+    }
+  }
+  return s0 + s1;
+}
+
+__device__ __forceinline__ float ldcg_now(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+// 16 values -> TMEM operand region columns [col, col + 16), hi/lo
+__device__ __forceinline__ void tm_store16(uint32_t tb, uint32_t lane_base, uint32_t col, const float v[16],
+                                           int mode3) {
+  uint32_t hi[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) hi[i] = tc::to_tf32(v[i]);
+  tc::tmem_st16(tb + lane_base + tc::kColAhi + col, hi);
+  if (mode3) {
+    uint32_t lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
+    tc::tmem_st16(tb + lane_base + tc::kColAlo + col, lo);
+  }
+}
+
+// D1 (dW^T of `layer`, unit-major) -> packed weight-gradient buffer
+__device__ __forceinline__ void flush_dw(uint32_t tb, uint32_t lane_base, int h, int k, int q, int layer,
+                                         const NvfiRenderGrads& D) {
+  if (layer > 0 || q == 0) {
+    float dwv[32];
+    tc::tmem_ld32(tb + lane_base + tc::kColD + 128u + (uint32_t)(h * 32), dwv);
+    float* wp = D.g_vel_w[layer] + k * NVFI_TM + h * 32;   // packed W^T gradient: [k][n]
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      red_add4(wp + 4 * j, dwv[4 * j + 0], dwv[4 * j + 1], dwv[4 * j + 2], dwv[4 * j + 3]);
+  }
+}
+
 // ---- backward through one weight-net evaluation -------------------------------------------
 // In: T.gout[n][m] = dL/d(basis weights), stash = the evaluation's pre-activations, (xs,ys,zs)[m]
 // and tval = its input.  Out: T.gout[0..2][m] = dL/d(x, y, z) through the network input; weight
-// and bias gradients added to the CTA's partials in `ws`.  Whole CTA (11 block barriers).
+// and bias gradients added to the packed gradient buffers.  Whole CTA (11 block barriers).
+//
+// Per layer l (4..0), with G_l in the TMEM operand region and G_l^T in shared memory:
+//   issuer: dX(l) MMAs -> D0                      workers: flush dW(l+1) from D1, db_l, prefetch h_{l-1}
+//   workers: G_{l-1} = D0 * silu'(h_{l-1}) parked in D0 (frees 32 registers);
+//            A_{l-1}^T (transposed stash read) -> operand region                       -- barrier B
+//   issuer: dW(l) MMAs -> D1
+//   workers: G_{l-1}: D0 -> operand region (lane = sample) and, transposed by 32 conflict-free
+//            scalar stores per thread, -> shared memory (row = unit)                   -- barrier C
 __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned char* gt_hi,
                             unsigned char* gt_lo, float* __restrict__ ws, const NvfiRenderGrads& D,
                             const float* stash, const float* xs, const float* ys, const float* zs,
@@ -215,15 +291,15 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == tc::kIssuerWarp) {
     const uint32_t gh = tc::uniform(tc::smem_u32(gt_hi)), gl = tc::uniform(tc::smem_u32(gt_lo));
-    __syncthreads();   // (A) head done: G_4 in TMEM and in the global copy
+    __syncthreads();   // (A) head done: G_4 in TMEM and G_4^T in shared memory
 #pragma unroll 1
     for (int l = 4; l >= 0; --l) {
       tc::tc_fence_after();
       issue_dx(c, is, l, mode3);
-      __syncthreads();   // (B) G_l^T in shared memory, A_{l-1}^T in TMEM
+      __syncthreads();   // (B) A_{l-1}^T in TMEM, D1 flushed
       tc::tc_fence_after();
       issue_dw(c, is, gh, gl, mode3);
-      __syncthreads();   // (C) G_{l-1} in TMEM and in the global copy
+      __syncthreads();   // (C) G_{l-1} in TMEM and G_{l-1}^T in shared memory
     }
     dphase += 10;
     return;
@@ -233,46 +309,52 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
   const int k = m;                             // unit   of this thread in the unit-major steps
   const uint32_t tb = c.tmem_base;
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-  float* gbuf = ws + TW_GBUF;
 
   TL(100);
-  // ---- head layer (128 -> 6), FP32 SIMT: G_4 -> TMEM + global copy; dW5, db5
+  // ---- head layer (128 -> 6), FP32 SIMT: G_4 -> TMEM + shared memory; dW5, db5
   {
+    const float4* hp = reinterpret_cast<const float4*>(stash + ((size_t)4 * NVFI_TM + m) * NVFI_TM + h * 32);
+    const float* tp = stash + ((size_t)4 * NVFI_TM + h * 32) * NVFI_TM + k;   // h4[32 h + i][k]
+    float4 hv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hv[j] = ldcg4_now(hp + j);
+    float at[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) at[i] = ldcg_now(tp + (size_t)i * NVFI_TM);
     float gw[6];
 #pragma unroll
     for (int n = 0; n < 6; ++n) gw[n] = T.gout[n][m];
-    const float4* hp = reinterpret_cast<const float4*>(stash + ((size_t)4 * NVFI_TM + m) * NVFI_TM + h * 32);
     float v[32];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float4 hv[4];
+    for (int j = 0; j < 8; ++j) {
+      const float hh[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) hv[j] = ldcg4_now(hp + half * 4 + j);
+      for (int i = 0; i < 4; ++i) {
+        const int kk = h * 32 + j * 4 + i;
+        float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float hh[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int kk = h * 32 + half * 16 + j * 4 + i;
-          float s = 0.f;
-#pragma unroll
-          for (int n = 0; n < 6; ++n) s = fmaf(gw[n], T.w5s[n][kk], s);
-          v[half * 16 + j * 4 + i] = s * silu_d(hh[i]);
-        }
+        for (int n = 0; n < 6; ++n) s = fmaf(gw[n], T.w5s[n][kk], s);
+        v[j * 4 + i] = s * silu_d(hh[i]);
       }
     }
     tm_store32(tb, lane_base, h, v, mode3);
-    float4* gp = reinterpret_cast<float4*>(gbuf + (size_t)m * NVFI_TM + h * 32);   // copy 0 = G_4
-#pragma unroll
-    for (int j = 0; j < 8; ++j) __stcg(gp + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+    gt_store_col32(gt_hi, gt_lo, q, lane, h, v, mode3);
+    fence_async_smem();
     // dW5^T[k][n] = sum_m silu(h4[m][k]) gout[n][m], this thread: unit k, samples [32 h, +32)
     float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int i = 0; i < 32; ++i) {
-      const int mm = h * 32 + i;
-      const float a = silu_v(__ldcg(stash + ((size_t)4 * NVFI_TM + mm) * NVFI_TM + k));
 #pragma unroll
-      for (int n = 0; n < 6; ++n) acc[n] = fmaf(a, T.gout[n][mm], acc[n]);
+    for (int half = 0; half < 2; ++half) {
+      if (half == 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) at[i] = ldcg_now(tp + (size_t)(16 + i) * NVFI_TM);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int mm = h * 32 + half * 16 + i;
+        const float a = silu_v(at[i]);
+#pragma unroll
+        for (int n = 0; n < 6; ++n) acc[n] = fmaf(a, T.gout[n][mm], acc[n]);
+      }
     }
 #pragma unroll
     for (int n = 0; n < 6; ++n) acc_head[n] += acc[n];   // flushed once, at kernel end
@@ -286,52 +368,42 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
 
 #pragma unroll 1
   for (int l = 4; l >= 0; --l) {
-    const float* gsrc = gbuf + (size_t)((4 - l) & 1) * kLayerF;        // G_l
-    float* gdst = gbuf + (size_t)((5 - l) & 1) * kLayerF;              // G_{l-1}
-    // ---- while the dX MMAs run: G_l^T into shared memory (unit n = k, samples [32 h, +32)),
-    //      bias gradient db_l[n] = sum_m G_l[m][n]
-    {
-      float v[32];
-      float s = 0.f;
+    // ---- under the dX MMAs: prefetch the rows of h_{l-1}, flush dW of layer l+1, bias gradient
+    float4 hv[8];
+    if (l > 0) {
+      const float4* hp = reinterpret_cast<const float4*>(stash + ((size_t)(l - 1) * NVFI_TM + m) * NVFI_TM + h * 32);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        v[i] = __ldcg(gsrc + (size_t)(h * 32 + i) * NVFI_TM + k);
-        s += v[i];
-      }
-      op_store_row32(gt_hi, gt_lo, k, h, v, mode3);
-      acc_bias[l] += s;   // unit k, samples [32 h, +32): flushed once, at kernel end
-      fence_async_smem();
+      for (int j = 0; j < 8; ++j) hv[j] = ldcg4_now(hp + j);
     }
+    if (l < 4) flush_dw(tb, lane_base, h, k, q, l + 1, D);
+    acc_bias[l] += gt_row_sum(gt_hi, gt_lo, k, h, mode3);   // unit k, samples [32 h, +32)
     TL(110 + l);
     tc::mbar_wait(&c.dbar, dphase & 1);   // dX accumulator
     ++dphase;
     tc::tc_fence_after();
     TL(120 + l);
-    // ---- dX epilogue (sample-major): G_{l-1} in registers, global copy; or the encoder chain rule
-    float gnew[32];
+    // ---- dX epilogue (sample-major): G_{l-1} = D0 * silu'(h_{l-1}), parked in D0
     if (l > 0) {
-      const float4* hp = reinterpret_cast<const float4*>(stash + ((size_t)(l - 1) * NVFI_TM + m) * NVFI_TM + h * 32);
-      float4* gp = reinterpret_cast<float4*>(gdst + (size_t)m * NVFI_TM + h * 32);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {     // 16 columns at a time: 4 loads in flight, 48 live registers
-        float4 hv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) hv[j] = ldcg4_now(hp + half * 4 + j);
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t dcol = tb + lane_base + tc::kColD + (uint32_t)(h * 32 + half * 16);
         float part[16];
-        tc::tmem_ld16(tb + lane_base + tc::kColD + (uint32_t)(h * 32 + half * 16), part);
+        tc::tmem_ld16(dcol, part);
+        uint32_t gq[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int b = half * 16 + 4 * j;
-          gnew[b + 0] = part[4 * j + 0] * silu_d(hv[j].x);
-          gnew[b + 1] = part[4 * j + 1] * silu_d(hv[j].y);
-          gnew[b + 2] = part[4 * j + 2] * silu_d(hv[j].z);
-          gnew[b + 3] = part[4 * j + 3] * silu_d(hv[j].w);
-          __stcg(gp + half * 4 + j, make_float4(gnew[b], gnew[b + 1], gnew[b + 2], gnew[b + 3]));
+          const float4 hh = hv[half * 4 + j];
+          gq[4 * j + 0] = __float_as_uint(part[4 * j + 0] * silu_d(hh.x));
+          gq[4 * j + 1] = __float_as_uint(part[4 * j + 1] * silu_d(hh.y));
+          gq[4 * j + 2] = __float_as_uint(part[4 * j + 2] * silu_d(hh.z));
+          gq[4 * j + 3] = __float_as_uint(part[4 * j + 3] * silu_d(hh.w));
         }
+        tc::tmem_st16(dcol, gq);
       }
     } else if (h == 0) {
       // dL/d(encoding) -> dL/d(x, y, z)  (encoder tangents)
-      tc::tmem_ld32(tb + lane_base + tc::kColD, gnew);
+      float ge[32];
+      tc::tmem_ld32(tb + lane_base + tc::kColD, ge);
       const float qv[3] = {xs[m], ys[m], zs[m]};
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -339,26 +411,30 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
         tc::sincos_bounded(qv[i], s1, c1);
         tc::sincos_bounded(qv[i] * 2.f, s2, c2);
         tc::sincos_bounded(qv[i] * 4.f, s4, c4);
-        T.gout[i][m] = gnew[i] + gnew[4 + i] * c1 - gnew[8 + i] * s1 +
-                       2.f * (gnew[12 + i] * c2 - gnew[16 + i] * s2) +
-                       4.f * (gnew[20 + i] * c4 - gnew[24 + i] * s4);
+        T.gout[i][m] = ge[i] + ge[4 + i] * c1 - ge[8 + i] * s1 +
+                       2.f * (ge[12 + i] * c2 - ge[16 + i] * s2) +
+                       4.f * (ge[20 + i] * c4 - ge[24 + i] * s4);
       }
     }
     TL(130 + l);
-    // ---- A_{l-1}^T into the TMEM operand region (the dX MMAs have finished reading G_l there)
+    // ---- A_{l-1}^T into the TMEM operand region (the dX MMAs have finished reading G_l there):
+    //      unit k of samples [32 h, +32), read transposed from the stash (coalesced across the warp)
     {
-      float v[32];
-      if (l > 0) {
-        const float* sp = stash + (size_t)(l - 1) * kLayerF + k;
+      const float* sp = (l > 0) ? stash + (size_t)(l - 1) * kLayerF + (size_t)(h * 32) * NVFI_TM + k
+                                : stash + (size_t)5 * kLayerF + (size_t)(h * 32) * 32 + (k & 31);
+      const int stride = (l > 0) ? NVFI_TM : 32;
+      const bool live = (l > 0) || (k < 32);
+      float a0[16], a1[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = silu_v(__ldcg(sp + (size_t)(h * 32 + i) * NVFI_TM));
-      } else {
-        // encoding^T from the copy the forward recompute stashed: unit k < 32 of samples [32 h, +32)
-        const float* ep = stash + (size_t)5 * kLayerF + k;   // enc[m][32] follows the 5 layers
+      for (int i = 0; i < 16; ++i) a0[i] = ldcg_now(sp + (size_t)i * stride);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = (k < 32) ? __ldcg(ep + (size_t)(h * 32 + i) * 32) : 0.f;
-      }
-      tm_store32(tb, lane_base, h, v, mode3);
+      for (int i = 0; i < 16; ++i) a1[i] = ldcg_now(sp + (size_t)(16 + i) * stride);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a0[i] = (l > 0) ? silu_v(a0[i]) : (live ? a0[i] : 0.f);
+      tm_store16(tb, lane_base, (uint32_t)(h * 32), a0, mode3);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a1[i] = (l > 0) ? silu_v(a1[i]) : (live ? a1[i] : 0.f);
+      tm_store16(tb, lane_base, (uint32_t)(h * 32 + 16), a1, mode3);
       tc::tmem_st_wait();
     }
     TL(140 + l);
@@ -369,17 +445,13 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
     ++dphase;
     tc::tc_fence_after();
     TL(160 + l);
-    // ---- dW^T flush (unit-major) and G_{l-1} into the TMEM operand region (sample-major)
-    if (l > 0 || q == 0) {
-      float dwv[32];
-      tc::tmem_ld32(tb + lane_base + tc::kColD + 128u + (uint32_t)(h * 32), dwv);
-      float* wp = D.g_vel_w[l] + k * NVFI_TM + h * 32;   // packed W^T gradient: [k][n]
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        red_add4(wp + 4 * j, dwv[4 * j + 0], dwv[4 * j + 1], dwv[4 * j + 2], dwv[4 * j + 3]);
-    }
+    // ---- G_{l-1}: D0 -> operand region (sample-major) and -> shared memory (transposed)
     if (l > 0) {
-      tm_store32(tb, lane_base, h, gnew, mode3);
+      float g[32];
+      tc::tmem_ld32(tb + lane_base + tc::kColD + (uint32_t)(h * 32), g);
+      tm_store32(tb, lane_base, h, g, mode3);
+      gt_store_col32(gt_hi, gt_lo, q, lane, h, g, mode3);
+      fence_async_smem();
       tc::tmem_st_wait();
     }
     TL(170 + l);
@@ -387,6 +459,7 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
     __syncthreads();   // (C)
     TL(180 + l);
   }
+  flush_dw(tb, lane_base, h, k, q, 0, D);
 }
 
 // v = basis(w, x): dL/dw and the explicit dL/dx from dL/dv (as in backward.cu)
