@@ -57,6 +57,7 @@ struct BwdTile {
   int q_idx[NVFI_TM + NT];
   int warp_cnt[2][NT / 32];
   int batch;
+  tc::Issuer iss;           // weight-ring state of the issuer warp (kept out of the workers' registers)
 };
 
 // Development aid: when a buffer is registered with nvfi_debug_timeline, thread 0 of CTA 0
@@ -220,6 +221,20 @@ __device__ __forceinline__ void gt_store_col32(unsigned char* t_hi, unsigned cha
   }
 }
 
+// 16-column variant: units [32 h + 16 half, +16)
+__device__ __forceinline__ void gt_store_col16(unsigned char* t_hi, unsigned char* t_lo, int q, int lane,
+                                               int h, int half, const float v[16], int mode3) {
+  const uint32_t base = (uint32_t)((q << 14) + (h << 12) + (half << 11) + ((lane & 3) << 2));
+  const uint32_t lc = (uint32_t)(lane >> 2);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t off = base + (uint32_t)(((i >> 3) << 10) + ((i & 7) << 7)) + ((lc ^ (uint32_t)(i & 7)) << 4);
+    const float hi = __uint_as_float(tc::to_tf32(v[i]));
+    *reinterpret_cast<float*>(t_hi + off) = hi;
+    if (mode3) *reinterpret_cast<float*>(t_lo + off) = v[i] - hi;
+  }
+}
+
 // Thread (unit k, sample block h): sum over the 32 samples of block h of row k of the G^T tile.
 __device__ __forceinline__ float gt_row_sum(const unsigned char* t_hi, const unsigned char* t_lo, int k, int h,
                                             int mode3) {
@@ -227,10 +242,11 @@ __device__ __forceinline__ float gt_row_sum(const unsigned char* t_hi, const uns
   float s0 = 0.f, s1 = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float4 a = *reinterpret_cast<const float4*>(t_hi + row + (j << 4));
+    const uint32_t ch = (uint32_t)((j ^ (k & 7)) << 4);   // lane-rotated chunk order: conflict-free
+    const float4 a = *reinterpret_cast<const float4*>(t_hi + row + ch);
     s0 += (a.x + a.y) + (a.z + a.w);
     if (mode3) {
-      const float4 b = *reinterpret_cast<const float4*>(t_lo + row + (j << 4));
+      const float4 b = *reinterpret_cast<const float4*>(t_lo + row + ch);
       s1 += (b.x + b.y) + (b.z + b.w);
     }
   }
@@ -262,12 +278,15 @@ __device__ __forceinline__ void tm_store16(uint32_t tb, uint32_t lane_base, uint
 __device__ __forceinline__ void flush_dw(uint32_t tb, uint32_t lane_base, int h, int k, int q, int layer,
                                          const NvfiRenderGrads& D) {
   if (layer > 0 || q == 0) {
-    float dwv[32];
-    tc::tmem_ld32(tb + lane_base + tc::kColD + 128u + (uint32_t)(h * 32), dwv);
     float* wp = D.g_vel_w[layer] + k * NVFI_TM + h * 32;   // packed W^T gradient: [k][n]
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      red_add4(wp + 4 * j, dwv[4 * j + 0], dwv[4 * j + 1], dwv[4 * j + 2], dwv[4 * j + 3]);
+    for (int half = 0; half < 2; ++half) {
+      float dwv[16];
+      tc::tmem_ld16(tb + lane_base + tc::kColD + 128u + (uint32_t)(h * 32 + half * 16), dwv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        red_add4(wp + half * 16 + 4 * j, dwv[4 * j + 0], dwv[4 * j + 1], dwv[4 * j + 2], dwv[4 * j + 3]);
+    }
   }
 }
 
@@ -283,13 +302,14 @@ __device__ __forceinline__ void flush_dw(uint32_t tb, uint32_t lane_base, int h,
 //   issuer: dW(l) MMAs -> D1
 //   workers: G_{l-1}: D0 -> operand region (lane = sample) and, transposed by 32 conflict-free
 //            scalar stores per thread, -> shared memory (row = unit)                   -- barrier C
-__device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned char* gt_hi,
+__device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsigned char* gt_hi,
                             unsigned char* gt_lo, float* __restrict__ ws, const NvfiRenderGrads& D,
                             const float* stash, const float* xs, const float* ys, const float* zs,
                             float tval, uint32_t& dphase, int mode3, float (&acc_head)[6],
                             float (&acc_bias)[6]) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == tc::kIssuerWarp) {
+    tc::Issuer is = is_shared;   // ring state: registers while issuing, shared memory between calls
     const uint32_t gh = tc::uniform(tc::smem_u32(gt_hi)), gl = tc::uniform(tc::smem_u32(gt_lo));
     __syncthreads();   // (A) head done: G_4 in TMEM and G_4^T in shared memory
 #pragma unroll 1
@@ -302,6 +322,7 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
       __syncthreads();   // (C) G_{l-1} in TMEM and G_{l-1}^T in shared memory
     }
     dphase += 10;
+    is_shared = is;
     return;
   }
   const int q = warp & 3, h = warp >> 2;
@@ -315,39 +336,36 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
   {
     const float4* hp = reinterpret_cast<const float4*>(stash + ((size_t)4 * NVFI_TM + m) * NVFI_TM + h * 32);
     const float* tp = stash + ((size_t)4 * NVFI_TM + h * 32) * NVFI_TM + k;   // h4[32 h + i][k]
-    float4 hv[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) hv[j] = ldcg4_now(hp + j);
-    float at[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) at[i] = ldcg_now(tp + (size_t)i * NVFI_TM);
     float gw[6];
 #pragma unroll
     for (int n = 0; n < 6; ++n) gw[n] = T.gout[n][m];
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float hh[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int kk = h * 32 + j * 4 + i;
-        float s = 0.f;
-#pragma unroll
-        for (int n = 0; n < 6; ++n) s = fmaf(gw[n], T.w5s[n][kk], s);
-        v[j * 4 + i] = s * silu_d(hh[i]);
-      }
-    }
-    tm_store32(tb, lane_base, h, v, mode3);
-    gt_store_col32(gt_hi, gt_lo, q, lane, h, v, mode3);
-    fence_async_smem();
-    // dW5^T[k][n] = sum_m silu(h4[m][k]) gout[n][m], this thread: unit k, samples [32 h, +32)
     float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
+    // two passes of 16 columns / 16 samples (not unrolled: bounded register use; each pass has all
+    // of its 20 loads in flight at once)
+#pragma unroll 1
     for (int half = 0; half < 2; ++half) {
-      if (half == 1) {
+      float4 hv[4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) at[i] = ldcg_now(tp + (size_t)(16 + i) * NVFI_TM);
+      for (int j = 0; j < 4; ++j) hv[j] = ldcg4_now(hp + half * 4 + j);
+      float at[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) at[i] = ldcg_now(tp + (size_t)(half * 16 + i) * NVFI_TM);
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float hh[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int kk = h * 32 + half * 16 + j * 4 + i;
+          float s = 0.f;
+#pragma unroll
+          for (int n = 0; n < 6; ++n) s = fmaf(gw[n], T.w5s[n][kk], s);
+          v[j * 4 + i] = s * silu_d(hh[i]);
+        }
       }
+      tm_store16(tb, lane_base, (uint32_t)(h * 32 + half * 16), v, mode3);
+      gt_store_col16(gt_hi, gt_lo, q, lane, h, half, v, mode3);
+      // dW5^T[k][n] = sum_m silu(h4[m][k]) gout[n][m], this thread: unit k, samples [32 h + 16 half, +16)
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int mm = h * 32 + half * 16 + i;
@@ -356,6 +374,7 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
         for (int n = 0; n < 6; ++n) acc[n] = fmaf(a, T.gout[n][mm], acc[n]);
       }
     }
+    fence_async_smem();
 #pragma unroll
     for (int n = 0; n < 6; ++n) acc_head[n] += acc[n];   // flushed once, at kernel end
     if (warp < 6)     // db5[n] = sum_m gout[n][m]: warp n, each lane 4 samples (reduced at kernel end)
@@ -447,10 +466,13 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is, BwdTile& T, unsigned cha
     TL(160 + l);
     // ---- G_{l-1}: D0 -> operand region (sample-major) and -> shared memory (transposed)
     if (l > 0) {
-      float g[32];
-      tc::tmem_ld32(tb + lane_base + tc::kColD + (uint32_t)(h * 32), g);
-      tm_store32(tb, lane_base, h, g, mode3);
-      gt_store_col32(gt_hi, gt_lo, q, lane, h, g, mode3);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float g[16];
+        tc::tmem_ld16(tb + lane_base + tc::kColD + (uint32_t)(h * 32 + half * 16), g);
+        tm_store16(tb, lane_base, (uint32_t)(h * 32 + half * 16), g, mode3);
+        gt_store_col16(gt_hi, gt_lo, q, lane, h, half, g, mode3);
+      }
       fence_async_smem();
       tc::tmem_st_wait();
     }
@@ -532,8 +554,9 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
     T.w5s[n][kk] = __ldg(F.vel_net[5].wt + (size_t)kk * F.vel_net[5].n_pad + n);
   }
   __syncthreads();
-  tc::Issuer is;
-  is.init(ctl, tc::smem_u32(ring), kBwdStages);
+  tc::Issuer& is = T.iss;
+  if (warp == tc::kIssuerWarp) is.init(ctl, tc::smem_u32(ring), kBwdStages);
+  __syncthreads();
   uint32_t dphase = 0, kphase = 0;
 
   int sub = NVFI_SUBS;
