@@ -23,6 +23,8 @@
 //       (registers -> global copy -> TMEM) and adds D1 to the CTA's partial weight gradient.
 //   The 6-wide head layer and the position-encoding chain rule are FP32 SIMT (tiny).
 // All GEMMs use the 3-term TF32 split (FP32-grade) unless the single-pass mode is selected.
+#include <cstdlib>
+
 #include "backward_common.cuh"
 #include "mlp_tc.cuh"
 
@@ -38,9 +40,15 @@ constexpr int kLayerF = NVFI_TM * NVFI_TM;  // 16384 floats
 // gradient buffers with red.global.add (no per-CTA partials, no reduce kernels).
 constexpr int kStashF = 5 * kLayerF + 32 * NVFI_TM;   // [5 layers][m][n] + enc[m][32]
 constexpr int TW_STASH = 0;                     // [2 evals][kStashF]
-constexpr int TW_GBUF = TW_STASH + 2 * kStashF; // [2][m][n] copies of G_l
-constexpr int TW_XSTEPS = TW_GBUF + 2 * kLayerF;
+constexpr int TW_XSTEPS = TW_STASH + 2 * kStashF;
 constexpr int TW_TOTAL = TW_XSTEPS + MAX_RK2_STEPS * 3 * NVFI_TM;
+// How the per-tile dW^T accumulator (128 x 128 FP32 in TMEM) reaches the packed gradient (bits 8..
+// of the kernel's `mode` argument).  red.global.add costs the LSU ~1 cycle per ELEMENT (16 K
+// cycles per layer and tile, measured; private per-CTA partials, atomic or plain read-modify-write,
+// were slower still), so the product path stages the tile in shared memory and lets the TMA engine
+// reduce it into L2: cp.reduce.async.bulk .add.f32, one 512-byte row per operation.
+enum { FLUSH_RED = 0, FLUSH_TMA = 1 };
+constexpr uint32_t kStagePitch = 528;   // staging row pitch (512 B + 16 B): conflict-free float4 stores
 
 struct BwdTile {
   float x0[3][NVFI_TM];
@@ -274,11 +282,11 @@ __device__ __forceinline__ void tm_store16(uint32_t tb, uint32_t lane_base, uint
   }
 }
 
-// D1 (dW^T of `layer`, unit-major) -> packed weight-gradient buffer
+// D1 (dW^T of `layer`, unit-major) -> packed weight gradient [k][n] by red.global.add (FLUSH_RED)
 __device__ __forceinline__ void flush_dw(uint32_t tb, uint32_t lane_base, int h, int k, int q, int layer,
                                          const NvfiRenderGrads& D) {
   if (layer > 0 || q == 0) {
-    float* wp = D.g_vel_w[layer] + k * NVFI_TM + h * 32;   // packed W^T gradient: [k][n]
+    float* wp = D.g_vel_w[layer] + k * NVFI_TM + h * 32;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       float dwv[16];
@@ -289,6 +297,17 @@ __device__ __forceinline__ void flush_dw(uint32_t tb, uint32_t lane_base, int h,
     }
   }
 }
+
+// TMA bulk reduction shared memory -> global (f32 add performed in L2), bulk async-group completion
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
+               "r"(tc::smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // ---- backward through one weight-net evaluation -------------------------------------------
 // In: T.gout[n][m] = dL/d(basis weights), stash = the evaluation's pre-activations, (xs,ys,zs)[m]
@@ -306,7 +325,7 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
                             unsigned char* gt_lo, float* __restrict__ ws, const NvfiRenderGrads& D,
                             const float* stash, const float* xs, const float* ys, const float* zs,
                             float tval, uint32_t& dphase, int mode3, float (&acc_head)[6],
-                            float (&acc_bias)[6]) {
+                            float (&acc_bias)[6], int flush_tma) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == tc::kIssuerWarp) {
     tc::Issuer is = is_shared;   // ring state: registers while issuing, shared memory between calls
@@ -334,8 +353,10 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
   TL(100);
   // ---- head layer (128 -> 6), FP32 SIMT: G_4 -> TMEM + shared memory; dW5, db5
   {
-    const float4* hp = reinterpret_cast<const float4*>(stash + ((size_t)4 * NVFI_TM + m) * NVFI_TM + h * 32);
-    const float* tp = stash + ((size_t)4 * NVFI_TM + h * 32) * NVFI_TM + k;   // h4[32 h + i][k]
+    // stash[l][unit][sample]: the sample-major reads (this thread = sample m) are coalesced scalar
+    // loads; the unit-major reads (this thread = unit k) are 16-byte loads of its own row
+    const float* hp = stash + ((size_t)4 * NVFI_TM + h * 32) * NVFI_TM + m;                    // h4[m][32 h + i]
+    const float4* tp = reinterpret_cast<const float4*>(stash + ((size_t)4 * NVFI_TM + k) * NVFI_TM + h * 32);
     float gw[6];
 #pragma unroll
     for (int n = 0; n < 6; ++n) gw[n] = T.gout[n][m];
@@ -344,24 +365,20 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
     // of its 20 loads in flight at once)
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
-      float4 hv[4];
+      float hv[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) hv[j] = ldcg4_now(hp + half * 4 + j);
-      float at[16];
+      for (int i = 0; i < 16; ++i) hv[i] = ldcg_now(hp + (size_t)(half * 16 + i) * NVFI_TM);
+      float4 at4[4];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) at[i] = ldcg_now(tp + (size_t)(half * 16 + i) * NVFI_TM);
+      for (int j = 0; j < 4; ++j) at4[j] = ldcg4_now(tp + half * 4 + j);
       float v[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float hh[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w};
+      for (int i = 0; i < 16; ++i) {
+        const int kk = h * 32 + half * 16 + i;
+        float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int kk = h * 32 + half * 16 + j * 4 + i;
-          float s = 0.f;
-#pragma unroll
-          for (int n = 0; n < 6; ++n) s = fmaf(gw[n], T.w5s[n][kk], s);
-          v[j * 4 + i] = s * silu_d(hh[i]);
-        }
+        for (int n = 0; n < 6; ++n) s = fmaf(gw[n], T.w5s[n][kk], s);
+        v[i] = s * silu_d(hv[i]);
       }
       tm_store16(tb, lane_base, (uint32_t)(h * 32 + half * 16), v, mode3);
       gt_store_col16(gt_hi, gt_lo, q, lane, h, half, v, mode3);
@@ -369,7 +386,8 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int mm = h * 32 + half * 16 + i;
-        const float a = silu_v(at[i]);
+        const float4 a4 = at4[i >> 2];
+        const float a = silu_v((i & 3) == 0 ? a4.x : ((i & 3) == 1 ? a4.y : ((i & 3) == 2 ? a4.z : a4.w)));
 #pragma unroll
         for (int n = 0; n < 6; ++n) acc[n] = fmaf(a, T.gout[n][mm], acc[n]);
       }
@@ -387,22 +405,42 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
 
 #pragma unroll 1
   for (int l = 4; l >= 0; --l) {
-    // ---- under the dX MMAs: prefetch the rows of h_{l-1}, flush dW of layer l+1, bias gradient
-    float4 hv[8];
+    // ---- under the dX MMAs: prefetch row k of the unit-major stash (A_{l-1}^T: unit k, samples
+    //      [32 h, +32) = 128 contiguous bytes per thread, 32 lines per warp instruction: the slow
+    //      access goes where it is hidden), bias gradient; FLUSH_RED: dW of layer l+1
+    float4 r[8];
     if (l > 0) {
-      const float4* hp = reinterpret_cast<const float4*>(stash + ((size_t)(l - 1) * NVFI_TM + m) * NVFI_TM + h * 32);
+      const float4* sp = reinterpret_cast<const float4*>(stash + ((size_t)(l - 1) * NVFI_TM + k) * NVFI_TM + h * 32);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) hv[j] = ldcg4_now(hp + j);
+      for (int j = 0; j < 8; ++j) r[j] = ldcg4_now(sp + j);
     }
-    if (l < 4) flush_dw(tb, lane_base, h, k, q, l + 1, D);
+    if (l < 4 && !flush_tma) flush_dw(tb, lane_base, h, k, q, l + 1, D);
     acc_bias[l] += gt_row_sum(gt_hi, gt_lo, k, h, mode3);   // unit k, samples [32 h, +32)
     TL(110 + l);
     tc::mbar_wait(&c.dbar, dphase & 1);   // dX accumulator
     ++dphase;
     tc::tc_fence_after();
     TL(120 + l);
-    // ---- dX epilogue (sample-major): G_{l-1} = D0 * silu'(h_{l-1}), parked in D0
     if (l > 0) {
+      // h_{l-1}[m][32 h + i] for the epilogue: coalesced scalar loads, in flight while A^T is stored
+      float hv[32];
+      const float* hp = stash + ((size_t)(l - 1) * NVFI_TM + h * 32) * NVFI_TM + m;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) hv[i] = ldcg_now(hp + (size_t)i * NVFI_TM);
+      // ---- A_{l-1}^T = silu(h_{l-1})^T into the TMEM operand region (the dX MMAs are done with G_l)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float a[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 rr = r[half * 4 + j];
+          a[4 * j + 0] = silu_v(rr.x); a[4 * j + 1] = silu_v(rr.y);
+          a[4 * j + 2] = silu_v(rr.z); a[4 * j + 3] = silu_v(rr.w);
+        }
+        tm_store16(tb, lane_base, (uint32_t)(h * 32 + half * 16), a, mode3);
+      }
+      TL(130 + l);
+      // ---- dX epilogue (sample-major): G_{l-1} = D0 * silu'(h_{l-1}), parked in D0
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const uint32_t dcol = tb + lane_base + tc::kColD + (uint32_t)(h * 32 + half * 16);
@@ -410,52 +448,45 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
         tc::tmem_ld16(dcol, part);
         uint32_t gq[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 hh = hv[half * 4 + j];
-          gq[4 * j + 0] = __float_as_uint(part[4 * j + 0] * silu_d(hh.x));
-          gq[4 * j + 1] = __float_as_uint(part[4 * j + 1] * silu_d(hh.y));
-          gq[4 * j + 2] = __float_as_uint(part[4 * j + 2] * silu_d(hh.z));
-          gq[4 * j + 3] = __float_as_uint(part[4 * j + 3] * silu_d(hh.w));
-        }
+        for (int i = 0; i < 16; ++i) gq[i] = __float_as_uint(part[i] * silu_d(hv[half * 16 + i]));
         tc::tmem_st16(dcol, gq);
       }
-    } else if (h == 0) {
-      // dL/d(encoding) -> dL/d(x, y, z)  (encoder tangents)
-      float ge[32];
-      tc::tmem_ld32(tb + lane_base + tc::kColD, ge);
-      const float qv[3] = {xs[m], ys[m], zs[m]};
+    } else {
+      // encoding^T from the copy the forward recompute stashed (enc[m][32]): unit k < 32
+      {
+        const float* sp = stash + (size_t)5 * kLayerF + (size_t)(h * 32) * 32 + (k & 31);
+        const bool live = k < 32;
+        float a0[16], a1[16];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        float s1, c1, s2, c2, s4, c4;
-        tc::sincos_bounded(qv[i], s1, c1);
-        tc::sincos_bounded(qv[i] * 2.f, s2, c2);
-        tc::sincos_bounded(qv[i] * 4.f, s4, c4);
-        T.gout[i][m] = ge[i] + ge[4 + i] * c1 - ge[8 + i] * s1 +
-                       2.f * (ge[12 + i] * c2 - ge[16 + i] * s2) +
-                       4.f * (ge[20 + i] * c4 - ge[24 + i] * s4);
+        for (int i = 0; i < 16; ++i) a0[i] = ldcg_now(sp + (size_t)i * 32);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a1[i] = ldcg_now(sp + (size_t)(16 + i) * 32);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a0[i] = live ? a0[i] : 0.f;
+        tm_store16(tb, lane_base, (uint32_t)(h * 32), a0, mode3);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a1[i] = live ? a1[i] : 0.f;
+        tm_store16(tb, lane_base, (uint32_t)(h * 32 + 16), a1, mode3);
+      }
+      TL(130 + l);
+      if (h == 0) {
+        // dL/d(encoding) -> dL/d(x, y, z)  (encoder tangents)
+        float ge[32];
+        tc::tmem_ld32(tb + lane_base + tc::kColD, ge);
+        const float qv[3] = {xs[m], ys[m], zs[m]};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          float s1, c1, s2, c2, s4, c4;
+          tc::sincos_bounded(qv[i], s1, c1);
+          tc::sincos_bounded(qv[i] * 2.f, s2, c2);
+          tc::sincos_bounded(qv[i] * 4.f, s4, c4);
+          T.gout[i][m] = ge[i] + ge[4 + i] * c1 - ge[8 + i] * s1 +
+                         2.f * (ge[12 + i] * c2 - ge[16 + i] * s2) +
+                         4.f * (ge[20 + i] * c4 - ge[24 + i] * s4);
+        }
       }
     }
-    TL(130 + l);
-    // ---- A_{l-1}^T into the TMEM operand region (the dX MMAs have finished reading G_l there):
-    //      unit k of samples [32 h, +32), read transposed from the stash (coalesced across the warp)
-    {
-      const float* sp = (l > 0) ? stash + (size_t)(l - 1) * kLayerF + (size_t)(h * 32) * NVFI_TM + k
-                                : stash + (size_t)5 * kLayerF + (size_t)(h * 32) * 32 + (k & 31);
-      const int stride = (l > 0) ? NVFI_TM : 32;
-      const bool live = (l > 0) || (k < 32);
-      float a0[16], a1[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) a0[i] = ldcg_now(sp + (size_t)i * stride);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) a1[i] = ldcg_now(sp + (size_t)(16 + i) * stride);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) a0[i] = (l > 0) ? silu_v(a0[i]) : (live ? a0[i] : 0.f);
-      tm_store16(tb, lane_base, (uint32_t)(h * 32), a0, mode3);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) a1[i] = (l > 0) ? silu_v(a1[i]) : (live ? a1[i] : 0.f);
-      tm_store16(tb, lane_base, (uint32_t)(h * 32 + 16), a1, mode3);
-      tc::tmem_st_wait();
-    }
+    tc::tmem_st_wait();
     TL(140 + l);
     tc::tc_fence_before();
     __syncthreads();   // (B)
@@ -464,8 +495,51 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
     ++dphase;
     tc::tc_fence_after();
     TL(160 + l);
-    // ---- G_{l-1}: D0 -> operand region (sample-major) and -> shared memory (transposed)
-    if (l > 0) {
+    if (flush_tma) {
+      // ---- dW^T of layer l: D1 -> staging rows in the (now dead) G^T region -> one TMA bulk
+      //      reduce-add per 512-byte row into the packed gradient; meanwhile G_{l-1}: D0 -> operand
+      //      region.  The G^T tile is rewritten only after the TMA engine has read the staging rows.
+      const bool rows = (l > 0) || (q == 0);
+      if (rows) {
+        unsigned char* srow = gt_hi + (size_t)k * kStagePitch + h * 128;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float dwv[16];
+          tc::tmem_ld16(tb + lane_base + tc::kColD + 128u + (uint32_t)(h * 32 + half * 16), dwv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(srow + half * 64 + j * 16) =
+                make_float4(dwv[4 * j + 0], dwv[4 * j + 1], dwv[4 * j + 2], dwv[4 * j + 3]);
+        }
+      }
+      fence_async_smem();
+      workers_sync();
+      if (h == 0 && rows) {
+        bulk_reduce_add_f32(D.g_vel_w[l] + k * NVFI_TM, gt_hi + (size_t)k * kStagePitch, 512u);
+        bulk_commit();
+      }
+      if (l > 0) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float g[16];
+          tc::tmem_ld16(tb + lane_base + tc::kColD + (uint32_t)(h * 32 + half * 16), g);
+          tm_store16(tb, lane_base, (uint32_t)(h * 32 + half * 16), g, mode3);
+        }
+      }
+      if (h == 0 && rows) bulk_wait_read0();
+      workers_sync();
+      if (l > 0) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float g[16];
+          tc::tmem_ld16(tb + lane_base + tc::kColD + (uint32_t)(h * 32 + half * 16), g);
+          gt_store_col16(gt_hi, gt_lo, q, lane, h, half, g, mode3);
+        }
+        fence_async_smem();
+        tc::tmem_st_wait();
+      }
+    } else if (l > 0) {
+      // ---- G_{l-1}: D0 -> operand region (sample-major) and -> shared memory (transposed)
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         float g[16];
@@ -481,7 +555,7 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
     __syncthreads();   // (C)
     TL(180 + l);
   }
-  flush_dw(tb, lane_base, h, k, q, 0, D);
+  if (!flush_tma) flush_dw(tb, lane_base, h, k, q, 0, D);
 }
 
 // v = basis(w, x): dL/dw and the explicit dL/dx from dL/dv (as in backward.cu)
@@ -516,8 +590,8 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
   BwdTile& T = *reinterpret_cast<BwdTile*>(reinterpret_cast<unsigned char*>(&ctl) + sizeof(tc::Ctl));
   float* ws = D.workspace + (size_t)blockIdx.x * WS_CTA_F;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int mode3 = (mode == NVFI_MLP_TF32X3) ? 1 : 0;
-
+  const int mode3 = ((mode & 0xff) == NVFI_MLP_TF32X3) ? 1 : 0;
+  const int flush_mode = mode >> 8;
   // uniform RK2 schedule of this render call (models/tensorf_keyframe.py:577-609)
   float sched_dt[MAX_RK2_STEPS], sched_t[MAX_RK2_STEPS];
   int n_steps = 0;
@@ -675,7 +749,7 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
       const float* zs = at_mid ? T.xm[2] : T.x0[2];
       if (kind == K_BWD2 || kind == K_BWD1) {
         bwd_eval_tc(ctl, is, T, g_hi, g_lo, ws, D, at_mid ? stash + kStashF : stash, xs, ys, zs,
-                    at_mid ? tmid : tcur, dphase, mode3, acc_head, acc_bias);
+                    at_mid ? tmid : tcur, dphase, mode3, acc_head, acc_bias, flush_mode == FLUSH_TMA);
       } else {
         TL(1);
         float* wout = (kind == K_FWD_A || kind == K_REV_A) ? &T.w0[0][0] : &T.w1[0][0];
@@ -756,6 +830,7 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
   }
   if (tid < NT) {
     const int kk = tid & 127;
+    bulk_wait0();   // outstanding TMA reductions of this thread (FLUSH_TMA) are complete
 #pragma unroll
     for (int n2 = 0; n2 < 6; ++n2) red_add(D.g_vel_w[5] + kk * 8 + n2, acc_head[n2]);
 #pragma unroll
@@ -805,6 +880,13 @@ extern "C" int nvfi_launch_advect_bwd_tc(const NvfiField* F, const NvfiRenderArg
   const int per_batch = NVFI_SUBS * tcb::NT;
   const int n_batches = (int)((total + per_batch - 1) / per_batch);
   const int grid = n_batches < sms ? n_batches : sms;
+  static int flush_mode = -1;
+  if (flush_mode < 0) {   // development switch (see the FLUSH_* enum); the default is the measured best
+    const char* e = getenv("NVFI_BWD_FLUSH");
+    flush_mode = e ? atoi(e) : tcb::FLUSH_TMA;
+    if (flush_mode < 0 || flush_mode > 1) flush_mode = tcb::FLUSH_TMA;
+  }
+  mode = (mode & 0xff) | (flush_mode << 8);
   NVFI_LAUNCH(tcb::k_advect_bwd_tc, grid, tc::kLaunchThreads, smem, st, *F, *A, *B, *D, S, total, n_batches, mode);
   return (int)cudaGetLastError();
 }
