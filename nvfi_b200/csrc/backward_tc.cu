@@ -399,6 +399,12 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
       acc_bias[5] += T.gout[warp][lane] + T.gout[warp][lane + 32] + T.gout[warp][lane + 64] + T.gout[warp][lane + 96];
     tc::tmem_st_wait();
   }
+  float4 rn[4];   // rows of the unit-major stash for the next A^T operand, loaded one phase ahead
+  {
+    const float4* sp = reinterpret_cast<const float4*>(stash + ((size_t)3 * NVFI_TM + k) * NVFI_TM + h * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rn[j] = ldcg4_now(sp + j);
+  }
   tc::tc_fence_before();
   __syncthreads();   // (A)
   TL(101);
@@ -409,13 +415,14 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
     //      [32 h, +32) = 128 contiguous bytes per thread, 32 lines per warp instruction: the slow
     //      access goes where it is hidden), bias gradient; FLUSH_RED: dW of layer l+1
     float4 r[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r[j] = rn[j];   // first half: issued in the previous dW window
     if (l > 0) {
       const float4* sp = reinterpret_cast<const float4*>(stash + ((size_t)(l - 1) * NVFI_TM + k) * NVFI_TM + h * 32);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = ldcg4_now(sp + j);
+      for (int j = 4; j < 8; ++j) r[j] = ldcg4_now(sp + j);
     }
     if (l < 4 && !flush_tma) flush_dw(tb, lane_base, h, k, q, l + 1, D);
-    acc_bias[l] += gt_row_sum(gt_hi, gt_lo, k, h, mode3);   // unit k, samples [32 h, +32)
     TL(110 + l);
     tc::mbar_wait(&c.dbar, dphase & 1);   // dX accumulator
     ++dphase;
@@ -491,6 +498,14 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
     tc::tc_fence_before();
     __syncthreads();   // (B)
     TL(150 + l);
+    // ---- under the dW MMAs: bias gradient from the G_l^T tile, first half of the next layer's
+    //      transposing loads
+    acc_bias[l] += gt_row_sum(gt_hi, gt_lo, k, h, mode3);   // unit k, samples [32 h, +32)
+    if (l > 1) {
+      const float4* sp = reinterpret_cast<const float4*>(stash + ((size_t)(l - 2) * NVFI_TM + k) * NVFI_TM + h * 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rn[j] = ldcg4_now(sp + j);
+    }
     tc::mbar_wait(&c.dbar, dphase & 1);   // dW accumulator
     ++dphase;
     tc::tc_fence_after();
