@@ -25,6 +25,8 @@ LIB_PATH = os.path.join(HERE, "libnvfi_b200.so")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
               "-Xptxas", "-v"]
+if os.environ.get("NVFI_TIMELINE"):     # development: phase timeline marks in the tensor-core backward
+    NVCC_FLAGS.append("-DNVFI_TIMELINE")
 
 
 def find_nvcc() -> str:

@@ -65,7 +65,10 @@ struct BwdTile {
   int q_idx[NVFI_TM + NT];
   int warp_cnt[2][NT / 32];
   int batch;
-  tc::Issuer iss;           // weight-ring state of the issuer warp (kept out of the workers' registers)
+  // weight-ring state of the issuer warp (kept out of the workers' registers).  Two rings: W^T
+  // blocks of the backward evaluations in the 2 dedicated stages, W blocks of the forward
+  // recomputation in 4 stages that alias the G^T tile (idle during forward evaluations).
+  tc::Issuer iss, iss_fwd;
 };
 
 // Development aid: when a buffer is registered with nvfi_debug_timeline, thread 0 of CTA 0
@@ -73,6 +76,7 @@ struct BwdTile {
 __device__ long long* g_tl_buf = nullptr;
 __device__ int g_tl_cap = 0;
 __device__ int g_tl_n = 0;
+#ifdef NVFI_TIMELINE
 __device__ __forceinline__ void TL(int tag) {
   if (blockIdx.x == 0 && threadIdx.x == 0 && g_tl_buf != nullptr) {
     const int i = g_tl_n;
@@ -83,6 +87,11 @@ __device__ __forceinline__ void TL(int tag) {
     }
   }
 }
+#else
+// compiled out of the product build: the pointer test alone costs every warp an L2 round trip
+// per call (measured: ~5 % of the kernel).  Build with -DNVFI_TIMELINE for tools/probe_timeline.py.
+__device__ __forceinline__ void TL(int) {}
+#endif
 
 // ld.global.cg as a volatile asm: consecutive calls are issued back to back (the compiler may not
 // sink one below the use of another, which it otherwise does under register pressure and turns
@@ -159,7 +168,7 @@ __device__ __forceinline__ void issue_dx(tc::Ctl& c, tc::Issuer& is, int layer, 
   const uint32_t d0 = is.tb + tc::kColD;
   for (uint32_t kb = 0; kb < 4; ++kb) {
     tc::ring_top_up(c, is, mode3);
-    tc::mbar_wait(&c.full[is.c_stage], is.c_round & 1);
+    tc::mbar_wait(&c.full[is.bar_base + is.c_stage], is.c_round & 1);
     tc::tc_fence_after();
     const uint32_t st = is.ring_u32 + is.c_stage * (uint32_t)tc::kStageBytes;
     const uint32_t w_hi = ((st >> 4) & 0x3FFFu) | (1u << 16);
@@ -176,7 +185,7 @@ __device__ __forceinline__ void issue_dx(tc::Ctl& c, tc::Issuer& is, int layer, 
           tc::mma_tf32_ts(d0, a_lo + ks * 8u, wh, idesc, 1u);
         }
       }
-      tc::tc_commit(&c.empty[is.c_stage]);
+      tc::tc_commit(&c.empty[is.bar_base + is.c_stage]);
       if (kb == 3) tc::tc_commit(&c.dbar);
     }
     __syncwarp();
@@ -330,6 +339,7 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
   if (warp == tc::kIssuerWarp) {
     tc::Issuer is = is_shared;   // ring state: registers while issuing, shared memory between calls
     const uint32_t gh = tc::uniform(tc::smem_u32(gt_hi)), gl = tc::uniform(tc::smem_u32(gt_lo));
+    tc::ring_top_up(c, is, mode3);   // W^T blocks stream in under the head phase
     __syncthreads();   // (A) head done: G_4 in TMEM and G_4^T in shared memory
 #pragma unroll 1
     for (int l = 4; l >= 0; --l) {
@@ -338,6 +348,7 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
       __syncthreads();   // (B) A_{l-1}^T in TMEM, D1 flushed
       tc::tc_fence_after();
       issue_dw(c, is, gh, gl, mode3);
+      tc::ring_top_up(c, is, mode3);   // both stages full again before the next dX
       __syncthreads();   // (C) G_{l-1} in TMEM and G_{l-1}^T in shared memory
     }
     dphase += 10;
@@ -423,6 +434,7 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
       for (int j = 4; j < 8; ++j) r[j] = ldcg4_now(sp + j);
     }
     if (l < 4 && !flush_tma) flush_dw(tb, lane_base, h, k, q, l + 1, D);
+    acc_bias[l] += gt_row_sum(gt_hi, gt_lo, k, h, mode3);   // bias gradient: unit k, samples [32 h, +32)
     TL(110 + l);
     tc::mbar_wait(&c.dbar, dphase & 1);   // dX accumulator
     ++dphase;
@@ -498,9 +510,7 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
     tc::tc_fence_before();
     __syncthreads();   // (B)
     TL(150 + l);
-    // ---- under the dW MMAs: bias gradient from the G_l^T tile, first half of the next layer's
-    //      transposing loads
-    acc_bias[l] += gt_row_sum(gt_hi, gt_lo, k, h, mode3);   // unit k, samples [32 h, +32)
+    // ---- under the dW MMAs: first half of the next layer's transposing loads
     if (l > 1) {
       const float4* sp = reinterpret_cast<const float4*>(stash + ((size_t)(l - 2) * NVFI_TM + k) * NVFI_TM + h * 32);
 #pragma unroll
@@ -644,7 +654,11 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
   }
   __syncthreads();
   tc::Issuer& is = T.iss;
-  if (warp == tc::kIssuerWarp) is.init(ctl, tc::smem_u32(ring), kBwdStages);
+  tc::Issuer& is_fwd = T.iss_fwd;
+  if (warp == tc::kIssuerWarp) {
+    is.init(ctl, tc::smem_u32(ring), kBwdStages, 0u, tc::RING_BWD);
+    is_fwd.init(ctl, tc::smem_u32(g_hi), 4u, kBwdStages, tc::RING_FWD);
+  }
   __syncthreads();
   uint32_t dphase = 0, kphase = 0;
 
@@ -769,7 +783,7 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
         TL(1);
         float* wout = (kind == K_FWD_A || kind == K_REV_A) ? &T.w0[0][0] : &T.w1[0][0];
         float* st = (kind == K_REV_A) ? stash : ((kind == K_REV_B) ? stash + kStashF : nullptr);
-        tc::vel_net_tile_tc<ACT_SILU>(ctl, is, 0, wout, xs, ys, zs, T.tvec, dphase, kphase, mode3, st);
+        tc::vel_net_tile_tc<ACT_SILU>(ctl, is_fwd, 0, wout, xs, ys, zs, T.tvec, dphase, kphase, mode3, st);
       }
       // ---- glue after the evaluation
       if (tid < NVFI_TM) {
@@ -855,7 +869,7 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
       if (lane == 0) red_add(D.g_vel_b[5] + warp, s5);
     }
   }
-  tc::teardown(ctl, is);
+  tc::teardown(ctl, is, &is_fwd);
   if (tid == 0 && n_done)
     atomicAdd(reinterpret_cast<unsigned long long*>(B.counters + 10), n_done);
 }
