@@ -23,8 +23,6 @@
 //       (registers -> global copy -> TMEM) and adds D1 to the CTA's partial weight gradient.
 //   The 6-wide head layer and the position-encoding chain rule are FP32 SIMT (tiny).
 // All GEMMs use the 3-term TF32 split (FP32-grade) unless the single-pass mode is selected.
-#include <cstdlib>
-
 #include "backward_common.cuh"
 #include "mlp_tc.cuh"
 
@@ -42,12 +40,11 @@ constexpr int kStashF = 5 * kLayerF + 32 * NVFI_TM;   // [5 layers][m][n] + enc[
 constexpr int TW_STASH = 0;                     // [2 evals][kStashF]
 constexpr int TW_XSTEPS = TW_STASH + 2 * kStashF;
 constexpr int TW_TOTAL = TW_XSTEPS + MAX_RK2_STEPS * 3 * NVFI_TM;
-// How the per-tile dW^T accumulator (128 x 128 FP32 in TMEM) reaches the packed gradient (bits 8..
-// of the kernel's `mode` argument).  red.global.add costs the LSU ~1 cycle per ELEMENT (16 K
-// cycles per layer and tile, measured; private per-CTA partials, atomic or plain read-modify-write,
-// were slower still), so the product path stages the tile in shared memory and lets the TMA engine
-// reduce it into L2: cp.reduce.async.bulk .add.f32, one 512-byte row per operation.
-enum { FLUSH_RED = 0, FLUSH_TMA = 1 };
+// The per-tile dW^T accumulator (128 x 128 FP32 in TMEM) reaches the packed gradient through the
+// TMA engine: staged in shared memory, then cp.reduce.async.bulk .add.f32 (the reduction runs in
+// L2), one 512-byte row per operation.  red.global.add from the threads costs the LSU ~1 cycle per
+// ELEMENT (16 K cycles per layer and tile, measured); private per-CTA partials, atomic or plain
+// read-modify-write, were slower still.
 constexpr uint32_t kStagePitch = 528;   // staging row pitch (512 B + 16 B): conflict-free float4 stores
 
 struct BwdTile {
@@ -101,16 +98,11 @@ __device__ __forceinline__ float4 ldcg4_now(const float4* p) {
   asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
-
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void red_add(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-}
-__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
-               : "memory");
 }
 __device__ __forceinline__ float sigmoid_fast(float h) {   // ex2.approx + rcp.approx, no fix-up code
   float e, r;
@@ -123,41 +115,6 @@ __device__ __forceinline__ float silu_d(float h) {   // SiLU'(h) = s + h s (1 - 
   return fmaf(h * s, 1.f - s, s);
 }
 __device__ __forceinline__ float silu_v(float h) { return h * sigmoid_fast(h); }
-
-// Thread (row r, 32-wide K block h): write 32 values of row r, columns [32 h, +32) of a
-// 128 x 128 FP32 operand tile, split hi/lo.  Layout: four K blocks of 16 KB, rows of 128 bytes,
-// 8-row groups of 1 KB, 16-byte chunks XOR-swizzled with the row (K-major SWIZZLE_128B).
-__device__ __forceinline__ void op_store_row32(unsigned char* t_hi, unsigned char* t_lo, int r, int h,
-                                               const float v[32], int mode3) {
-  const uint32_t row = (uint32_t)((h << 14) + ((r >> 3) << 10) + ((r & 7) << 7));
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float4 hi, lo;
-    float t;
-    t = __uint_as_float(tc::to_tf32(v[4 * j + 0])); hi.x = t; lo.x = v[4 * j + 0] - t;
-    t = __uint_as_float(tc::to_tf32(v[4 * j + 1])); hi.y = t; lo.y = v[4 * j + 1] - t;
-    t = __uint_as_float(tc::to_tf32(v[4 * j + 2])); hi.z = t; lo.z = v[4 * j + 2] - t;
-    t = __uint_as_float(tc::to_tf32(v[4 * j + 3])); hi.w = t; lo.w = v[4 * j + 3] - t;
-    const uint32_t off = row + (uint32_t)((j ^ (r & 7)) << 4);
-    *reinterpret_cast<float4*>(t_hi + off) = hi;
-    if (mode3) *reinterpret_cast<float4*>(t_lo + off) = lo;
-  }
-}
-
-// Thread (TMEM lane, 32-column group h): store 32 values into the TMEM operand region, hi/lo.
-__device__ __forceinline__ void tm_store32(uint32_t tb, uint32_t lane_base, int h, const float v[32],
-                                           int mode3) {
-  uint32_t hi[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) hi[i] = tc::to_tf32(v[i]);
-  tc::tmem_st32(tb + lane_base + tc::kColAhi + (uint32_t)(h * 32), hi);
-  if (mode3) {
-    uint32_t lo[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
-    tc::tmem_st32(tb + lane_base + tc::kColAlo + (uint32_t)(h * 32), lo);
-  }
-}
 
 // ---- issuer warp ----------------------------------------------------------------------------
 // dX of layer l:  D0[m][k] = sum_n G[m][n] Wt[k][n]   A = G in TMEM, B = W^T image blocks (ring)
@@ -221,23 +178,6 @@ __device__ __forceinline__ void issue_dw(tc::Ctl& c, tc::Issuer& is, uint32_t gt
   __syncwarp();
 }
 
-// Thread (sample m = 32 q + lane, unit block h): 32 values G[m][32 h + i] -> column m of rows
-// 32 h + i of the K-major G^T operand tile (K = sample), split hi/lo.  A warp writes one 128-byte
-// row segment per store (32 consecutive samples of one unit): conflict-free, and the transpose
-// costs no memory round trip.
-__device__ __forceinline__ void gt_store_col32(unsigned char* t_hi, unsigned char* t_lo, int q, int lane,
-                                               int h, const float v[32], int mode3) {
-  const uint32_t base = (uint32_t)((q << 14) + (h << 12) + ((lane & 3) << 2));
-  const uint32_t lc = (uint32_t)(lane >> 2);
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const uint32_t off = base + (uint32_t)(((i >> 3) << 10) + ((i & 7) << 7)) + ((lc ^ (uint32_t)(i & 7)) << 4);
-    const float hi = __uint_as_float(tc::to_tf32(v[i]));
-    *reinterpret_cast<float*>(t_hi + off) = hi;
-    if (mode3) *reinterpret_cast<float*>(t_lo + off) = v[i] - hi;
-  }
-}
-
 // 16-column variant: units [32 h + 16 half, +16)
 __device__ __forceinline__ void gt_store_col16(unsigned char* t_hi, unsigned char* t_lo, int q, int lane,
                                                int h, int half, const float v[16], int mode3) {
@@ -291,22 +231,6 @@ __device__ __forceinline__ void tm_store16(uint32_t tb, uint32_t lane_base, uint
   }
 }
 
-// D1 (dW^T of `layer`, unit-major) -> packed weight gradient [k][n] by red.global.add (FLUSH_RED)
-__device__ __forceinline__ void flush_dw(uint32_t tb, uint32_t lane_base, int h, int k, int q, int layer,
-                                         const NvfiRenderGrads& D) {
-  if (layer > 0 || q == 0) {
-    float* wp = D.g_vel_w[layer] + k * NVFI_TM + h * 32;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float dwv[16];
-      tc::tmem_ld16(tb + lane_base + tc::kColD + 128u + (uint32_t)(h * 32 + half * 16), dwv);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        red_add4(wp + half * 16 + 4 * j, dwv[4 * j + 0], dwv[4 * j + 1], dwv[4 * j + 2], dwv[4 * j + 3]);
-    }
-  }
-}
-
 // TMA bulk reduction shared memory -> global (f32 add performed in L2), bulk async-group completion
 __device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssrc, uint32_t bytes) {
   asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
@@ -334,7 +258,7 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
                             unsigned char* gt_lo, float* __restrict__ ws, const NvfiRenderGrads& D,
                             const float* stash, const float* xs, const float* ys, const float* zs,
                             float tval, uint32_t& dphase, int mode3, float (&acc_head)[6],
-                            float (&acc_bias)[6], int flush_tma) {
+                            float (&acc_bias)[6]) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == tc::kIssuerWarp) {
     tc::Issuer is = is_shared;   // ring state: registers while issuing, shared memory between calls
@@ -424,17 +348,16 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
   for (int l = 4; l >= 0; --l) {
     // ---- under the dX MMAs: prefetch row k of the unit-major stash (A_{l-1}^T: unit k, samples
     //      [32 h, +32) = 128 contiguous bytes per thread, 32 lines per warp instruction: the slow
-    //      access goes where it is hidden), bias gradient; FLUSH_RED: dW of layer l+1
+    //      access goes where it is hidden), bias gradient
+    acc_bias[l] += gt_row_sum(gt_hi, gt_lo, k, h, mode3);   // bias gradient: unit k, samples [32 h, +32)
     float4 r[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) r[j] = rn[j];   // first half: issued in the previous dW window
-    if (l > 0) {
+    if (l > 0) {   // second half: last, so that nothing forces these registers out before they are used
       const float4* sp = reinterpret_cast<const float4*>(stash + ((size_t)(l - 1) * NVFI_TM + k) * NVFI_TM + h * 32);
 #pragma unroll
       for (int j = 4; j < 8; ++j) r[j] = ldcg4_now(sp + j);
     }
-    if (l < 4 && !flush_tma) flush_dw(tb, lane_base, h, k, q, l + 1, D);
-    acc_bias[l] += gt_row_sum(gt_hi, gt_lo, k, h, mode3);   // bias gradient: unit k, samples [32 h, +32)
     TL(110 + l);
     tc::mbar_wait(&c.dbar, dphase & 1);   // dX accumulator
     ++dphase;
@@ -520,7 +443,7 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
     ++dphase;
     tc::tc_fence_after();
     TL(160 + l);
-    if (flush_tma) {
+    {
       // ---- dW^T of layer l: D1 -> staging rows in the (now dead) G^T region -> one TMA bulk
       //      reduce-add per 512-byte row into the packed gradient; meanwhile G_{l-1}: D0 -> operand
       //      region.  The G^T tile is rewritten only after the TMA engine has read the staging rows.
@@ -563,24 +486,12 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
         fence_async_smem();
         tc::tmem_st_wait();
       }
-    } else if (l > 0) {
-      // ---- G_{l-1}: D0 -> operand region (sample-major) and -> shared memory (transposed)
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float g[16];
-        tc::tmem_ld16(tb + lane_base + tc::kColD + (uint32_t)(h * 32 + half * 16), g);
-        tm_store16(tb, lane_base, (uint32_t)(h * 32 + half * 16), g, mode3);
-        gt_store_col16(gt_hi, gt_lo, q, lane, h, half, g, mode3);
-      }
-      fence_async_smem();
-      tc::tmem_st_wait();
     }
     TL(170 + l);
     tc::tc_fence_before();
     __syncthreads();   // (C)
     TL(180 + l);
   }
-  if (!flush_tma) flush_dw(tb, lane_base, h, k, q, 0, D);
 }
 
 // v = basis(w, x): dL/dw and the explicit dL/dx from dL/dv (as in backward.cu)
@@ -615,8 +526,7 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
   BwdTile& T = *reinterpret_cast<BwdTile*>(reinterpret_cast<unsigned char*>(&ctl) + sizeof(tc::Ctl));
   float* ws = D.workspace + (size_t)blockIdx.x * WS_CTA_F;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int mode3 = ((mode & 0xff) == NVFI_MLP_TF32X3) ? 1 : 0;
-  const int flush_mode = mode >> 8;
+  const int mode3 = (mode == NVFI_MLP_TF32X3) ? 1 : 0;
   // uniform RK2 schedule of this render call (models/tensorf_keyframe.py:577-609)
   float sched_dt[MAX_RK2_STEPS], sched_t[MAX_RK2_STEPS];
   int n_steps = 0;
@@ -778,7 +688,7 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
       const float* zs = at_mid ? T.xm[2] : T.x0[2];
       if (kind == K_BWD2 || kind == K_BWD1) {
         bwd_eval_tc(ctl, is, T, g_hi, g_lo, ws, D, at_mid ? stash + kStashF : stash, xs, ys, zs,
-                    at_mid ? tmid : tcur, dphase, mode3, acc_head, acc_bias, flush_mode == FLUSH_TMA);
+                    at_mid ? tmid : tcur, dphase, mode3, acc_head, acc_bias);
       } else {
         TL(1);
         float* wout = (kind == K_FWD_A || kind == K_REV_A) ? &T.w0[0][0] : &T.w1[0][0];
@@ -859,7 +769,7 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
   }
   if (tid < NT) {
     const int kk = tid & 127;
-    bulk_wait0();   // outstanding TMA reductions of this thread (FLUSH_TMA) are complete
+    bulk_wait0();   // outstanding TMA reductions of this thread are complete
 #pragma unroll
     for (int n2 = 0; n2 < 6; ++n2) red_add(D.g_vel_w[5] + kk * 8 + n2, acc_head[n2]);
 #pragma unroll
@@ -909,13 +819,6 @@ extern "C" int nvfi_launch_advect_bwd_tc(const NvfiField* F, const NvfiRenderArg
   const int per_batch = NVFI_SUBS * tcb::NT;
   const int n_batches = (int)((total + per_batch - 1) / per_batch);
   const int grid = n_batches < sms ? n_batches : sms;
-  static int flush_mode = -1;
-  if (flush_mode < 0) {   // development switch (see the FLUSH_* enum); the default is the measured best
-    const char* e = getenv("NVFI_BWD_FLUSH");
-    flush_mode = e ? atoi(e) : tcb::FLUSH_TMA;
-    if (flush_mode < 0 || flush_mode > 1) flush_mode = tcb::FLUSH_TMA;
-  }
-  mode = (mode & 0xff) | (flush_mode << 8);
   NVFI_LAUNCH(tcb::k_advect_bwd_tc, grid, tc::kLaunchThreads, smem, st, *F, *A, *B, *D, S, total, n_batches, mode);
   return (int)cudaGetLastError();
 }
