@@ -356,11 +356,26 @@ def run_gpu(args):
                     ach = work / sec / 1e9
                     e.update(bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"])
             kern[name] = e
+        # DRAM traffic per launch: per-unit dram__bytes (read + write) of one `ncu --set full` capture
+        # (profiles/ncu_traffic.json, tools/ncu_traffic.py) x the units this run's launch processed
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            units = {"valid_samples": n_valid, "advected_samples": n_adv, "advected_samples_bwd": n_adv_bwd}
+            for kname, kv in tj.get("kernels", {}).items():
+                traffic[kname] = kv["dram_bytes_per_unit"] * units[kv["unit"]]
+            for kname, e in kern.items():
+                if kname.split("::")[-1] in traffic:
+                    e["traffic"] = traffic[kname.split("::")[-1]]
         top = next(iter(kern))
         r = dict(kern[top])
         line["roofline"] = {"kernel": top, "bound": r.get("bound"), "achieved": r.get("achieved"),
                             "peak": r.get("peak"), "unit": r.get("unit"), "frac": r.get("frac"),
-                            "traffic": None, "share_of_step": r["share"],
+                            "traffic": r.get("traffic"), "traffic_unit": "bytes/launch",
+                            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per unit "
+                                              "(profiles/ncu_traffic.json, 50-row capture) x units of this launch",
+                            "share_of_step": r["share"],
                             "peak_source": pk["source"] + ("; TF32 peak = 0.5 x measured sustained bf16"
                                                             if r.get("bound") == "tensor" else "")}
         line["roofline_gather"] = dict(kern.get("k_march", {}), kernel="k_march",

@@ -1,4 +1,8 @@
-"""Phase timeline of CTA 0 of the tensor-core backward (clock64 deltas between marks)."""
+"""Phase timeline of CTA 0 of the tensor-core backward (clock64 deltas between marks).
+
+The marks are compiled out of the product build: rebuild the library with
+    NVFI_TIMELINE=1 python -m nvfi_b200.build --force
+before sending this probe to the GPU box (and rebuild without it afterwards)."""
 import sys, os, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
