@@ -192,6 +192,18 @@ __device__ __forceinline__ void gt_store_col16(unsigned char* t_hi, unsigned cha
   }
 }
 
+// 16 already-split values (one of the hi / lo tiles) -> column m of rows 32 h + 16 half + i
+__device__ __forceinline__ void gt_store_raw16(unsigned char* tile, int q, int lane, int h, int half,
+                                               const float v[16]) {
+  const uint32_t base = (uint32_t)((q << 14) + (h << 12) + (half << 11) + ((lane & 3) << 2));
+  const uint32_t lc = (uint32_t)(lane >> 2);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t off = base + (uint32_t)(((i >> 3) << 10) + ((i & 7) << 7)) + ((lc ^ (uint32_t)(i & 7)) << 4);
+    *reinterpret_cast<float*>(tile + off) = v[i];
+  }
+}
+
 // Thread (unit k, sample block h): sum over the 32 samples of block h of row k of the G^T tile.
 __device__ __forceinline__ float gt_row_sum(const unsigned char* t_hi, const unsigned char* t_lo, int k, int h,
                                             int mode3) {
@@ -349,6 +361,44 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
     // ---- under the dX MMAs: prefetch row k of the unit-major stash (A_{l-1}^T: unit k, samples
     //      [32 h, +32) = 128 contiguous bytes per thread, 32 lines per warp instruction: the slow
     //      access goes where it is hidden), bias gradient
+    if (l < 4) {
+      // dW^T of layer l + 1: D1 -> staging rows in the dead G^T tile -> one TMA bulk reduce-add per
+      // 512-byte row into the packed gradient (all hidden layers above 0 have 128 rows)
+      {
+        unsigned char* srow = gt_hi + (size_t)k * kStagePitch + h * 128;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float dwv[16];
+          tc::tmem_ld16(tb + lane_base + tc::kColD + 128u + (uint32_t)(h * 32 + half * 16), dwv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(srow + half * 64 + j * 16) =
+                make_float4(dwv[4 * j + 0], dwv[4 * j + 1], dwv[4 * j + 2], dwv[4 * j + 3]);
+        }
+      }
+      fence_async_smem();
+      workers_sync();
+      if (h == 0) {
+        bulk_reduce_add_f32(D.g_vel_w[l + 1] + k * NVFI_TM, gt_hi + (size_t)k * kStagePitch, 512u);
+        bulk_commit();
+        bulk_wait_read0();
+      }
+      workers_sync();
+      // G_l^T tile for the dW MMAs: the operand region already holds G_l split hi | lo (the dX
+      // MMAs only read it), transposed by conflict-free scalar stores
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float g[16];
+        tc::tmem_ld16(tb + lane_base + tc::kColAhi + (uint32_t)(h * 32 + half * 16), g);
+        gt_store_raw16(gt_hi, q, lane, h, half, g);
+        if (mode3) {
+          tc::tmem_ld16(tb + lane_base + tc::kColAlo + (uint32_t)(h * 32 + half * 16), g);
+          gt_store_raw16(gt_lo, q, lane, h, half, g);
+        }
+      }
+      fence_async_smem();
+      workers_sync();
+    }
     acc_bias[l] += gt_row_sum(gt_hi, gt_lo, k, h, mode3);   // bias gradient: unit k, samples [32 h, +32)
     float4 r[8];
 #pragma unroll
@@ -443,55 +493,43 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
     ++dphase;
     tc::tc_fence_after();
     TL(160 + l);
-    {
-      // ---- dW^T of layer l: D1 -> staging rows in the (now dead) G^T region -> one TMA bulk
-      //      reduce-add per 512-byte row into the packed gradient; meanwhile G_{l-1}: D0 -> operand
-      //      region.  The G^T tile is rewritten only after the TMA engine has read the staging rows.
-      const bool rows = (l > 0) || (q == 0);
-      if (rows) {
-        unsigned char* srow = gt_hi + (size_t)k * kStagePitch + h * 128;
+    // ---- G_{l-1}: D0 -> operand region, split hi | lo; the next dX starts right after barrier C
+    //      (the dW flush and the G^T tile follow under its MMAs)
+    if (l > 0) {
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float dwv[16];
-          tc::tmem_ld16(tb + lane_base + tc::kColD + 128u + (uint32_t)(h * 32 + half * 16), dwv);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(srow + half * 64 + j * 16) =
-                make_float4(dwv[4 * j + 0], dwv[4 * j + 1], dwv[4 * j + 2], dwv[4 * j + 3]);
-        }
+      for (int half = 0; half < 2; ++half) {
+        float g[16];
+        tc::tmem_ld16(tb + lane_base + tc::kColD + (uint32_t)(h * 32 + half * 16), g);
+        tm_store16(tb, lane_base, (uint32_t)(h * 32 + half * 16), g, mode3);
       }
-      fence_async_smem();
-      workers_sync();
-      if (h == 0 && rows) {
-        bulk_reduce_add_f32(D.g_vel_w[l] + k * NVFI_TM, gt_hi + (size_t)k * kStagePitch, 512u);
-        bulk_commit();
-      }
-      if (l > 0) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float g[16];
-          tc::tmem_ld16(tb + lane_base + tc::kColD + (uint32_t)(h * 32 + half * 16), g);
-          tm_store16(tb, lane_base, (uint32_t)(h * 32 + half * 16), g, mode3);
-        }
-      }
-      if (h == 0 && rows) bulk_wait_read0();
-      workers_sync();
-      if (l > 0) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float g[16];
-          tc::tmem_ld16(tb + lane_base + tc::kColD + (uint32_t)(h * 32 + half * 16), g);
-          gt_store_col16(gt_hi, gt_lo, q, lane, h, half, g, mode3);
-        }
-        fence_async_smem();
-        tc::tmem_st_wait();
-      }
+      tc::tmem_st_wait();
     }
     TL(170 + l);
     tc::tc_fence_before();
     __syncthreads();   // (C)
     TL(180 + l);
   }
+  // dW^T of layer 0 (32 rows: lane quadrant 0)
+  if (q == 0) {
+    unsigned char* srow = gt_hi + (size_t)k * kStagePitch + h * 128;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float dwv[16];
+      tc::tmem_ld16(tb + lane_base + tc::kColD + 128u + (uint32_t)(h * 32 + half * 16), dwv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4*>(srow + half * 64 + j * 16) =
+            make_float4(dwv[4 * j + 0], dwv[4 * j + 1], dwv[4 * j + 2], dwv[4 * j + 3]);
+    }
+  }
+  fence_async_smem();
+  workers_sync();
+  if (h == 0 && q == 0) {
+    bulk_reduce_add_f32(D.g_vel_w[0] + k * NVFI_TM, gt_hi + (size_t)k * kStagePitch, 512u);
+    bulk_commit();
+    bulk_wait_read0();   // the caller's next phase may overwrite the staging rows
+  }
+  workers_sync();
 }
 
 // v = basis(w, x): dL/dw and the explicit dL/dx from dL/dv (as in backward.cu)
