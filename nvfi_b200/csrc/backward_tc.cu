@@ -396,10 +396,8 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
           gt_store_raw16(gt_lo, q, lane, h, half, g);
         }
       }
-      fence_async_smem();
-      workers_sync();
+      fence_async_smem();   // visible to the dW MMAs (async proxy) and, after barrier B, to the bias sums
     }
-    acc_bias[l] += gt_row_sum(gt_hi, gt_lo, k, h, mode3);   // bias gradient: unit k, samples [32 h, +32)
     float4 r[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) r[j] = rn[j];   // first half: issued in the previous dW window
@@ -483,7 +481,9 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
     tc::tc_fence_before();
     __syncthreads();   // (B)
     TL(150 + l);
-    // ---- under the dW MMAs: first half of the next layer's transposing loads
+    // ---- under the dW MMAs: bias gradient from the G_l^T tile (the MMAs only read it), first half
+    //      of the next layer's transposing loads
+    acc_bias[l] += gt_row_sum(gt_hi, gt_lo, k, h, mode3);   // unit k, samples [32 h, +32)
     if (l > 1) {
       const float4* sp = reinterpret_cast<const float4*>(stash + ((size_t)(l - 2) * NVFI_TM + k) * NVFI_TM + h * 32);
 #pragma unroll
