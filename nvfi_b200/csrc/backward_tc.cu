@@ -411,13 +411,9 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
     ++dphase;
     tc::tc_fence_after();
     TL(120 + l);
+    // ---- A_{l-1}^T into the TMEM operand region (the dX MMAs are done with G_l): all the dW MMAs
+    //      wait for; the dX epilogue follows under them
     if (l > 0) {
-      // h_{l-1}[m][32 h + i] for the epilogue: coalesced scalar loads, in flight while A^T is stored
-      float hv[32];
-      const float* hp = stash + ((size_t)(l - 1) * NVFI_TM + h * 32) * NVFI_TM + m;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) hv[i] = ldcg_now(hp + (size_t)i * NVFI_TM);
-      // ---- A_{l-1}^T = silu(h_{l-1})^T into the TMEM operand region (the dX MMAs are done with G_l)
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         float a[16];
@@ -429,8 +425,35 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
         }
         tm_store16(tb, lane_base, (uint32_t)(h * 32 + half * 16), a, mode3);
       }
-      TL(130 + l);
-      // ---- dX epilogue (sample-major): G_{l-1} = D0 * silu'(h_{l-1}), parked in D0
+    } else {
+      // encoding^T from the copy the forward recompute stashed (enc[m][32]): unit k < 32
+      const float* sp = stash + (size_t)5 * kLayerF + (size_t)(h * 32) * 32 + (k & 31);
+      const bool live = k < 32;
+      float a0[16], a1[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a0[i] = ldcg_now(sp + (size_t)i * 32);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a1[i] = ldcg_now(sp + (size_t)(16 + i) * 32);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a0[i] = live ? a0[i] : 0.f;
+      tm_store16(tb, lane_base, (uint32_t)(h * 32), a0, mode3);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a1[i] = live ? a1[i] : 0.f;
+      tm_store16(tb, lane_base, (uint32_t)(h * 32 + 16), a1, mode3);
+    }
+    tc::tmem_st_wait();
+    TL(140 + l);
+    tc::tc_fence_before();
+    __syncthreads();   // (B)
+    TL(150 + l);
+    // ---- under the dW MMAs: the dX epilogue (sample-major) G_{l-1} = D0 * silu'(h_{l-1}), parked in
+    //      D0 (the dW MMAs accumulate in D1), or the encoder chain rule
+    if (l > 0) {
+      // h_{l-1}[m][32 h + i]: coalesced scalar loads of the unit-major stash
+      float hv[32];
+      const float* hp = stash + ((size_t)(l - 1) * NVFI_TM + h * 32) * NVFI_TM + m;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) hv[i] = ldcg_now(hp + (size_t)i * NVFI_TM);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const uint32_t dcol = tb + lane_base + tc::kColD + (uint32_t)(h * 32 + half * 16);
@@ -441,46 +464,23 @@ __device__ void bwd_eval_tc(tc::Ctl& c, tc::Issuer& is_shared, BwdTile& T, unsig
         for (int i = 0; i < 16; ++i) gq[i] = __float_as_uint(part[i] * silu_d(hv[half * 16 + i]));
         tc::tmem_st16(dcol, gq);
       }
-    } else {
-      // encoding^T from the copy the forward recompute stashed (enc[m][32]): unit k < 32
-      {
-        const float* sp = stash + (size_t)5 * kLayerF + (size_t)(h * 32) * 32 + (k & 31);
-        const bool live = k < 32;
-        float a0[16], a1[16];
+      tc::tmem_st_wait();
+    } else if (h == 0) {
+      // dL/d(encoding) -> dL/d(x, y, z)  (encoder tangents)
+      float ge[32];
+      tc::tmem_ld32(tb + lane_base + tc::kColD, ge);
+      const float qv[3] = {xs[m], ys[m], zs[m]};
 #pragma unroll
-        for (int i = 0; i < 16; ++i) a0[i] = ldcg_now(sp + (size_t)i * 32);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a1[i] = ldcg_now(sp + (size_t)(16 + i) * 32);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a0[i] = live ? a0[i] : 0.f;
-        tm_store16(tb, lane_base, (uint32_t)(h * 32), a0, mode3);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a1[i] = live ? a1[i] : 0.f;
-        tm_store16(tb, lane_base, (uint32_t)(h * 32 + 16), a1, mode3);
-      }
-      TL(130 + l);
-      if (h == 0) {
-        // dL/d(encoding) -> dL/d(x, y, z)  (encoder tangents)
-        float ge[32];
-        tc::tmem_ld32(tb + lane_base + tc::kColD, ge);
-        const float qv[3] = {xs[m], ys[m], zs[m]};
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          float s1, c1, s2, c2, s4, c4;
-          tc::sincos_bounded(qv[i], s1, c1);
-          tc::sincos_bounded(qv[i] * 2.f, s2, c2);
-          tc::sincos_bounded(qv[i] * 4.f, s4, c4);
-          T.gout[i][m] = ge[i] + ge[4 + i] * c1 - ge[8 + i] * s1 +
-                         2.f * (ge[12 + i] * c2 - ge[16 + i] * s2) +
-                         4.f * (ge[20 + i] * c4 - ge[24 + i] * s4);
-        }
+      for (int i = 0; i < 3; ++i) {
+        float s1, c1, s2, c2, s4, c4;
+        tc::sincos_bounded(qv[i], s1, c1);
+        tc::sincos_bounded(qv[i] * 2.f, s2, c2);
+        tc::sincos_bounded(qv[i] * 4.f, s4, c4);
+        T.gout[i][m] = ge[i] + ge[4 + i] * c1 - ge[8 + i] * s1 +
+                       2.f * (ge[12 + i] * c2 - ge[16 + i] * s2) +
+                       4.f * (ge[20 + i] * c4 - ge[24 + i] * s4);
       }
     }
-    tc::tmem_st_wait();
-    TL(140 + l);
-    tc::tc_fence_before();
-    __syncthreads();   // (B)
-    TL(150 + l);
     // ---- under the dW MMAs: bias gradient from the G_l^T tile (the MMAs only read it), first half
     //      of the next layer's transposing loads
     acc_bias[l] += gt_row_sum(gt_hi, gt_lo, k, h, mode3);   // unit k, samples [32 h, +32)
