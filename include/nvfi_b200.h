@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NVFI_ABI_VERSION 8
+#define NVFI_ABI_VERSION 9
 
 /* error codes */
 #define NVFI_OK 0
@@ -309,6 +309,21 @@ int nvfi_velocity(const NvfiField* field, const float* xyzt, int64_t n, int32_t 
 int nvfi_pde_loss(const NvfiField* field, const float* xyzt, const float* va, int64_t n,
                   double* loss_sums, const NvfiPdeGrads* grads, int32_t want_grad,
                   int32_t* counters, void* stream);
+
+/* ---- plane regularisers (one streaming pass: loss term + gradient) --------------------------
+ * TVLoss.forward (utils/tensorf_utils.py:139-158) of one NCHW plane (1, C, H, W), as called by
+ * TV_loss_density / TV_loss_app (models/tensorf_keyframe.py:205-231; `time_plane` = the t=True
+ * variant, which weights the H differences by 3):
+ *   *loss_accum += scale * 2 * (tfac * sum (x[y+1] - x[y])^2 / (C (H-1) W) + sum (x[.,x+1] - x[.,x])^2 / (C H (W-1)))
+ * and, when grad != NULL, grad (same shape, overwritten) = d(that term)/dx.  `scale` carries
+ * TVLoss_weight and the 1e-2 factor of the callers.  loss_accum: device double. */
+int nvfi_tv_loss(const float* plane, int C, int H, int W, int time_plane, float scale,
+                 double* loss_accum, float* grad, void* stream);
+/* density_L1 (models/tensorf_keyframe.py:188-203): *loss_accum += scale * mean |x - offset| over n
+ * elements (offset 0 for space planes, 1 for time planes); grad (n, overwritten) optional.
+ * plane and grad must be 16-byte aligned. */
+int nvfi_l1_loss(const float* plane, int64_t n, float offset, float scale, double* loss_accum,
+                 float* grad, void* stream);
 
 /* ---- development probe -------------------------------------------------------------------
  * One 128x128x128 TF32 tcgen05 MMA, D[k][n] = sum_m At[k][m] G[m][n], A from tensor memory and

@@ -12,7 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnvfi_b200.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 VEL_LAYERS = 6
 MAX_MASK_LAYERS = 8
 
@@ -129,6 +129,8 @@ SIGNATURES = {
     "nvfi_velocity": (_i, [C.POINTER(NvfiField), _vp, _i64, _i, _vp, _vp, _vp]),
     "nvfi_debug_mma_mn": (_i, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
     "nvfi_debug_timeline": (_i, [_vp, _i]),
+    "nvfi_tv_loss": (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "nvfi_l1_loss": (_i, [_vp, _i64, _f, _f, _vp, _vp, _vp]),
     "nvfi_pde_loss": (_i, [C.POINTER(NvfiField), _vp, _vp, _i64, _vp, C.POINTER(NvfiPdeGrads), _i, _vp, _vp]),
 }
 

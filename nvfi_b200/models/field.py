@@ -241,24 +241,36 @@ class TensorVMKeyframeTimeKplane(nn.Module):
 
     # ---------------------------------------------------------------- regularisers (torch)
     def density_L1(self):
+        """models/tensorf_keyframe.py:188-203.  CUDA planes: one fused pass per plane
+        (nvfi_b200/regularizers.py); host tensors keep the reference's torch expression."""
+        if self.density_plane_space[0].is_cuda:
+            from .. import regularizers as R
+            return R.density_l1(list(self.density_plane_space), list(self.density_plane_time))
         total = 0
         for k in range(3):
             total = total + torch.mean(torch.abs(self.density_plane_space[k])) \
                 + torch.mean(torch.abs(1 - self.density_plane_time[k]))
         return total
 
-    def TV_loss_density(self, reg):
+    def _tv(self, reg, space, time, with_time):
+        """`reg` is the caller's TVLoss (utils/tensorf_utils.py:139-158).  A TVLoss-like object
+        (it exposes TVLoss_weight) on CUDA planes takes the fused kernel; any other callable is
+        applied as the reference applies it."""
+        if space[0].is_cuda and hasattr(reg, "TVLoss_weight"):
+            from .. import regularizers as R
+            return R.tv_loss(list(space), list(time), float(reg.TVLoss_weight), with_time)
         total = 0
         for k in range(3):
-            total = total + reg(self.density_plane_space[k]) * 1e-2 \
-                + ((reg(self.density_plane_time[k], t=True) * 1e-2) if self.num_keyframes > 1 else 0)
+            total = total + reg(space[k]) * 1e-2 + ((reg(time[k], t=True) * 1e-2) if with_time else 0)
         return total
 
+    def TV_loss_density(self, reg):
+        """models/tensorf_keyframe.py:205-217."""
+        return self._tv(reg, self.density_plane_space, self.density_plane_time, self.num_keyframes > 1)
+
     def TV_loss_app(self, reg):
-        total = 0
-        for k in range(3):
-            total = total + reg(self.app_plane_space[k]) * 1e-2
-        return total
+        """models/tensorf_keyframe.py:219-231 (the time-plane term is commented out upstream)."""
+        return self._tv(reg, self.app_plane_space, self.app_plane_time, False)
 
     # ---------------------------------------------------------------- maintenance
     @torch.no_grad()
