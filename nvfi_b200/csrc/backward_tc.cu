@@ -550,7 +550,7 @@ __device__ __forceinline__ void basis_bwd(const float w[6], float x, float y, fl
 // (a 112-register build fails to launch).
 __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
     k_advect_bwd_tc(const __grid_constant__ NvfiField F, const NvfiRenderArgs A, const NvfiRenderBuffers B,
-                    const NvfiRenderGrads D, int S, long long total, int n_batches, int mode) {
+                    const NvfiRenderGrads D, int S, long long total, int n_batches, int mode, int subs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char* p = smem_raw;
   {
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
   __syncthreads();
   uint32_t dphase = 0, kphase = 0;
 
-  int sub = NVFI_SUBS;
+  int sub = subs;
   long long batch_base = 0;
   bool exhausted = false;
   int qc = 0, par = 0;
@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
 
   for (;;) {
     while (qc < NVFI_TM && !exhausted) {
-      if (sub == NVFI_SUBS) {
+      if (sub == subs) {
         if (tid == 0) T.batch = atomicAdd(&B.counters[3], 1);
         __syncthreads();
         const int b = T.batch;
@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
           exhausted = true;
           break;
         }
-        batch_base = (long long)b * (NVFI_SUBS * NT);
+        batch_base = (long long)b * ((long long)subs * NT);
         sub = 0;
       }
       const long long idx = batch_base + (long long)sub * NT + tid;
@@ -854,9 +854,10 @@ extern "C" int nvfi_launch_advect_bwd_tc(const NvfiField* F, const NvfiRenderArg
                                       (int)smem));
     cached = smem;
   }
-  const int per_batch = NVFI_SUBS * tcb::NT;
+  const int subs = grab_subs(total, tcb::NT, sms);
+  const int per_batch = subs * tcb::NT;
   const int n_batches = (int)((total + per_batch - 1) / per_batch);
   const int grid = n_batches < sms ? n_batches : sms;
-  NVFI_LAUNCH(tcb::k_advect_bwd_tc, grid, tc::kLaunchThreads, smem, st, *F, *A, *B, *D, S, total, n_batches, mode);
+  NVFI_LAUNCH(tcb::k_advect_bwd_tc, grid, tc::kLaunchThreads, smem, st, *F, *A, *B, *D, S, total, n_batches, mode, subs);
   return (int)cudaGetLastError();
 }

@@ -41,6 +41,14 @@
 
 namespace nvfi {
 
+// Sub-batches (of `threads` raw samples) per atomically grabbed batch of the persistent
+// compaction kernels: NVFI_SUBS when there is plenty of work, fewer when the launch would
+// otherwise have fewer than ~6 batches per SM.
+inline int grab_subs(long long total, int threads, int sms) {
+  const long long subs = total / ((long long)threads * sms * 6);
+  return (int)(subs < 1 ? 1 : (subs > NVFI_SUBS ? NVFI_SUBS : subs));
+}
+
 // Host side: counts a kernel launch and, when profiling is on, times it (prof.cu).
 // Used through NVFI_LAUNCH.
 struct ProfScope {

@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(256) k_sample_only(const NvfiField F, const Nv
 template <class Mlp>
 __device__ __forceinline__ void sample_advect_body(const NvfiField& F, const NvfiRenderArgs& A,
                                                    const NvfiRenderBuffers& B, int S,
-                                                   long long total, int n_batches, int mode) {
+                                                   long long total, int n_batches, int mode,
+                                                   int subs = NVFI_SUBS) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Mlp mlp;
   mlp.init(smem_raw, F.vel_net, nullptr, mode);
@@ -144,7 +145,7 @@ __device__ __forceinline__ void sample_advect_body(const NvfiField& F, const Nvf
   SampleAdvectTail<NT>& sm = *reinterpret_cast<SampleAdvectTail<NT>*>(smem_raw + Mlp::kBytes);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  int sub = NVFI_SUBS;
+  int sub = subs;
   long long batch_base = 0;
   bool exhausted = false;
   unsigned n_valid = 0;
@@ -155,7 +156,7 @@ __device__ __forceinline__ void sample_advect_body(const NvfiField& F, const Nvf
   for (;;) {
     // ---- produce: fill the queue up to one tile
     while (qc < NVFI_TM && !exhausted) {
-      if (sub == NVFI_SUBS) {
+      if (sub == subs) {
         if (tid == 0) sm.q.batch = atomicAdd(&B.counters[0], 1);
         __syncthreads();
         const int b = sm.q.batch;
@@ -164,7 +165,7 @@ __device__ __forceinline__ void sample_advect_body(const NvfiField& F, const Nvf
           exhausted = true;
           break;
         }
-        batch_base = (long long)b * (NVFI_SUBS * NT);
+        batch_base = (long long)b * ((long long)subs * NT);
         sub = 0;
       }
       const long long idx = batch_base + (long long)sub * NT + tid;
@@ -235,8 +236,8 @@ __global__ void __launch_bounds__(NVFI_THREADS, 2)
 
 __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
     k_sample_advect_tc(const __grid_constant__ NvfiField F, const NvfiRenderArgs A,
-                       const NvfiRenderBuffers B, int S, long long total, int n_batches, int mode) {
-  sample_advect_body<TcMlp>(F, A, B, S, total, n_batches, mode);
+                       const NvfiRenderBuffers B, int S, long long total, int n_batches, int mode, int subs) {
+  sample_advect_body<TcMlp>(F, A, B, S, total, n_batches, mode, subs);
 }
 
 // Chunk-global predicate of sample_ray (models/tensorf_base.py:294): one flag per chunk
@@ -444,14 +445,17 @@ extern "C" int nvfi_launch_sample_advect(const NvfiField* F, const NvfiRenderArg
   const int mode = nvfi_get_mlp_mode();
   if (mode != NVFI_MLP_FP32_SIMT) {
     if (!has_umma(F->vel_net)) return NVFI_EINVAL;
-    const int per_batch = NVFI_SUBS * TcMlp::kThreads;
+    // raw samples per atomically grabbed batch: 8 x 512 for a frame, fewer for a training batch
+    // (2 048 rays x 192 samples are 96 such batches: a third of the SMs would stay idle)
+    const int subs = grab_subs(total, TcMlp::kThreads, num_sms());
+    const int per_batch = subs * TcMlp::kThreads;
     const int n_batches = (int)((total + per_batch - 1) / per_batch);
     const size_t smem = TcMlp::kBytes + sizeof(SampleAdvectTail<TcMlp::kThreads>);
     static size_t cached = 0;
     int rc = set_smem(k_sample_advect_tc, smem, cached);
     if (rc != NVFI_OK) return rc;
     const int grid = min(n_batches, num_sms());
-    NVFI_LAUNCH(k_sample_advect_tc, grid, TcMlp::kLaunchThreads, smem, st, *F, *A, *B, S, total, n_batches, mode);
+    NVFI_LAUNCH(k_sample_advect_tc, grid, TcMlp::kLaunchThreads, smem, st, *F, *A, *B, S, total, n_batches, mode, subs);
     return (int)cudaGetLastError();
   }
   const int n_batches = (int)((total + NVFI_SUBS * NVFI_THREADS - 1) / (NVFI_SUBS * NVFI_THREADS));
