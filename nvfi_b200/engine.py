@@ -509,9 +509,22 @@ def integrate_pos(binding: FieldBinding, x: torch.Tensor, t: torch.Tensor, base:
     out = torch.empty_like(x)
     if n == 0:
         return out
+    # A 128-point tile runs as many RK2 steps as its slowest point (models/tensorf_keyframe.py:592-609:
+    # the loop ends when every offset is 0).  With per-point times (get_vel_loss draws t ~ U(0,1):
+    # 1 step inside [0, tmax], up to 10 beyond) almost every random tile contains a 10-step point, so
+    # the points are grouped by step count first; every point's arithmetic is unchanged.
+    order = None
+    if n >= 4 * 128:
+        steps = torch.ceil((t - base).abs() / float(s.dt_max)).to(torch.int32)
+        if int(steps.max()) > int(steps.min()) + 1:
+            order = torch.argsort(steps)
+            x, t, base = x[order].contiguous(), t[order].contiguous(), base[order].contiguous()
     cnt = _counters(x.device)
+    res = torch.empty_like(x) if order is not None else out
     L.check(L.load().nvfi_integrate_pos(C.byref(s), x.data_ptr(), t.data_ptr(), base.data_ptr(), n,
-                                        out.data_ptr(), cnt.data_ptr(), _stream()), "integrate_pos")
+                                        res.data_ptr(), cnt.data_ptr(), _stream()), "integrate_pos")
+    if order is not None:
+        out[order] = res
     return out
 
 
