@@ -171,3 +171,98 @@ def test_tensor_core_backward_matches_simt_backward_at_scale(scene):
     bad = {k: v for k, v in worst.items() if not v < 1e-4}
     assert not bad, bad
     nv.requires_grad_(False)
+
+
+def test_multi_step_backward_tc_matches_simt(scene):
+    """t = 1.0 > tmax: 10 RK2 steps per sample (models/tensorf_keyframe.py:592-609) — the tile
+    program of the tensor-core backward runs its forward sweep, two weight rings and 10 reverse
+    steps; compared with the FP32 SIMT backward."""
+    from nvfi_b200 import engine
+    cfg, nv, o, d = scene
+    nv.requires_grad_(True)
+    nv.nvfi.train()
+    oo, dd = _band(o, d, 4)            # 3 200 rays
+    n = oo.shape[0]
+    gen = torch.Generator().manual_seed(9)
+    jit = torch.rand(n, 1, generator=gen)
+    tgt = torch.rand(n, 3, generator=gen).cuda()
+
+    def grads():
+        nv.zero_grad(set_to_none=True)
+        rgb, *_ = nv.nvfi.render_rays(1.0, oo, dd, white_bg=True, ray_chunk=CHUNK, jitter=jit)
+        torch.nn.functional.mse_loss(rgb, tgt).backward()
+        return {k: p.grad.detach().clone() for k, p in nv.named_parameters() if p.grad is not None}
+
+    g_tc = grads()
+    prev = engine.set_mlp_mode("simt")
+    try:
+        g_simt = grads()
+    finally:
+        engine.set_mlp_mode(prev)
+    assert set(g_tc) == set(g_simt)
+    errs = {k: _nrel(g_tc[k], g_simt[k]) for k in g_tc}
+    # Ten RK2 steps amplify the last-bit differences of the two forward paths (x_adv agrees to
+    # 2e-7).  Everything downstream of the ReLUs of MLPRender_PE (its first two layers, basis_mat,
+    # the appearance planes) has a DIScontinuous gradient in x_adv — a hidden unit whose
+    # pre-activation crosses 0 switches its whole gradient — so those tensors agree only to ~1e-3
+    # (the reference's own FP32 autograd is off its FP64 value by the same 1e-3 there, see
+    # test_extrapolated_time_gradients_vs_fp64_oracle); everything else meets the 1e-4 gate.
+    kinked = ("app_plane", "basis_mat", "renderModule.mlp.0", "renderModule.mlp.2")
+    bad = {k: v for k, v in errs.items() if not v < (5e-3 if any(s_ in k for s_ in kinked) else 1e-4)}
+    assert not bad, bad
+    nv.requires_grad_(False)
+
+
+def test_extrapolated_time_gradients_vs_fp64_oracle():
+    """Train step at t = 1.0 (10 RK2 steps) on a 48^3 scene against the oracle evaluated in FLOAT64.
+    The FP32 autograd of the reference algorithm is itself 1e-3 away from this value for the tensors
+    behind the ReLUs of MLPRender_PE (measured: app planes 1.0e-3, basis_mat 6e-4, vel_net 1.6e-3);
+    the CUDA path has to meet the 1e-4 gate against the FP64 value."""
+    from nvfi_b200.scenes import build_scene, frame_rays
+    from oracle import nvfi_oracle as O
+    from oracle.scene_io import scene_from_state
+    grid = (48, 48, 48)
+    cfg, nv, sd = build_scene("bat", grid=grid, max_n_samples=64)
+    f = nv.nvfi
+    nv.requires_grad_(True)
+    f.train()
+    o, d = frame_rays(800, 800, crop=(368, 368, 64, 64))
+    gen = torch.Generator().manual_seed(0)
+    n = 1024
+    sel = torch.randperm(o.shape[0], generator=gen)[:n]
+    oo, dd = o[sel].contiguous(), d[sel].contiguous()
+    jit = torch.rand(n, 1, generator=gen)
+    tgt = torch.rand(n, 3, generator=gen)
+    rgb, *_ = f.render_rays(1.0, oo.cuda(), dd.cuda(), white_bg=True, ray_chunk=CHUNK, jitter=jit)
+    torch.nn.functional.mse_loss(rgb, tgt.cuda()).backward()
+    got = dict(nv.named_parameters())
+
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        sc = scene_from_state(cfg, list(grid), int(cfg.nvfi.num_keyframes), sd, requires_grad=True)
+
+        def cast(x):
+            if isinstance(x, torch.Tensor):
+                return x.detach().double().requires_grad_(True)
+            if isinstance(x, (list, tuple)):
+                return type(x)(cast(y) for y in x)
+            return x
+        for name in ("density_plane_space", "density_plane_time", "app_plane_space", "app_plane_time",
+                     "basis_mat", "render_mlp", "vel_net", "acc_net"):
+            setattr(sc, name, cast(getattr(sc, name)))
+        sc.aabb = sc.aabb.double()
+        ref = O.render_chunk(sc, 1.0, oo.double(), dd.double(), white_bg=True, training=True, jitter=jit.double())
+        torch.nn.functional.mse_loss(ref[0], tgt.double()).backward()
+    finally:
+        torch.set_default_dtype(prev)
+    pairs = {"nvfi.density_plane_space.0": sc.density_plane_space[0], "nvfi.app_plane_space.0": sc.app_plane_space[0],
+             "nvfi.app_plane_time.1": sc.app_plane_time[1], "nvfi.basis_mat.weight": sc.basis_mat,
+             "nvfi.renderModule.mlp.0.weight": sc.render_mlp[0][0], "nvfi.renderModule.mlp.2.weight": sc.render_mlp[1][0],
+             "nvfi.renderModule.mlp.4.weight": sc.render_mlp[2][0], "nvfi.vel_net.weight_net.1.weight": sc.vel_net[0][0],
+             "nvfi.vel_net.weight_net.4.0.weight": sc.vel_net[2][0]}
+    errs = {k: _nrel(got[k].grad.double().cpu(), r.grad) for k, r in pairs.items()}
+    print(errs)
+    assert float((rgb.detach().double().cpu() - ref[0].detach()).abs().max()) < 1e-4
+    bad = {k: v for k, v in errs.items() if not v < 1e-4}
+    assert not bad, bad
