@@ -151,7 +151,7 @@ __device__ __forceinline__ float dsigma_dfeat(const NvfiField& F, float sigma, f
 // k_density_bwd: one warp per ray, 8-lane groups per valid sample.
 // g_x_adv[sample] = (appearance part, already written for w > thres) + density part.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
     k_density_bwd(const NvfiField F, const NvfiRenderArgs A, const NvfiRenderBuffers B,
                   const NvfiRenderGrads D, int S) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -20,7 +20,7 @@ namespace nvfi {
 
 #define MARCH_WARPS 8
 
-__global__ void __launch_bounds__(MARCH_WARPS * 32)
+__global__ void __launch_bounds__(MARCH_WARPS * 32, 4)
     k_march(const NvfiField F, const NvfiRenderArgs A, const NvfiRenderBuffers B, int S,
             int s_pad) {
   extern __shared__ __align__(16) float sig_all[];
