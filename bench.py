@@ -384,6 +384,26 @@ def run_gpu(args):
         line["kernels"] = kern
         line["counts"] = {"valid_samples": n_valid, "advected_samples": n_adv, "app_samples": n_app,
                           "app_samples_bwd": n_app_bwd, "advected_samples_bwd": n_adv_bwd}
+        # secondary figure (SURVEY.md 8d ii): one 800x800 eval frame, mode='test', no gradients
+        try:
+            field.eval()
+            with torch.no_grad():
+                for _ in range(2):
+                    field.render_rays(T_RENDER, o_d, d_d, white_bg=True, ray_chunk=RAY_CHUNK)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    field.render_rays(T_RENDER, o_d, d_d, white_bg=True, ray_chunk=RAY_CHUNK)
+                e1.record()
+                torch.cuda.synchronize()
+            ms_eval = e0.elapsed_time(e1) / 3
+            line["eval_frame"] = {"ms": ms_eval, "rays_per_s": n / (ms_eval * 1e-3),
+                                  "note": "render only (mode='test'), rank 0, inputs resident"}
+        except Exception as exc:   # never lose the bench line over the secondary figure
+            line["eval_frame"] = {"error": str(exc)[:200]}
+        finally:
+            field.train()
         if world == 1 and not args.no_cpu:
             leg = CpuLeg()
             leg.run(0.0, 1)     # warm-up chunk (thread pool, allocator)
