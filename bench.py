@@ -18,8 +18,9 @@ Prints ONE JSON line (rank 0).  Keys (see DESIGN.md "Measurement"):
                 sample of the same workload, all host threads
   --impl reference  times only that CPU leg (the reference has no native code and cannot travel
                 to the GPU box; the oracle port is pinned to it by tests/golden/*)
-Multi-GPU: weak scaling — every rank renders its own 800x800 frame (a different camera of the
-same scene) and the ranks exchange ONE all-reduce of the flat gradient buffer per step.
+Multi-GPU: weak scaling — every rank renders its own 800x800 frame (same camera = identical work
+per GPU, rank-specific jitter and target) and the ranks exchange ONE all-reduce of the flat gradient
+buffer per step.
 """
 from __future__ import annotations
 
@@ -228,8 +229,10 @@ def run_gpu(args):
     assert field.nSamples == 192, field.nSamples
     nv.requires_grad_(True)
     renderer = M.Renderer(nv, 0, 0, RAY_CHUNK)
-    # weak scaling: every rank renders its own camera of the same scene
-    o_h, d_h = frame_rays(H, W, theta=30.0 + 9.0 * rank)
+    # weak scaling = fixed work per GPU: every rank renders an 800x800 frame of the SAME camera with
+    # its own stratified jitter and target (a different camera per rank changes the number of valid
+    # samples by up to 10 %, and max-over-ranks would then measure the scene, not the system)
+    o_h, d_h = frame_rays(H, W, theta=30.0)
     if args.rows != H:      # profiling aid: a horizontal band through the middle of the frame
         r0 = (H - args.rows) // 2
         o_h, d_h = o_h[r0 * W:(r0 + args.rows) * W].contiguous(), d_h[r0 * W:(r0 + args.rows) * W].contiguous()
