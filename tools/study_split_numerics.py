@@ -82,3 +82,53 @@ for scheme in ("fp32", "tf32", "tf32x3", "tf32+bf16", "fp16x3"):
     err = (out - truth).abs()
     print(f"  {scheme:10s} max abs {float(err.max()):.2e}  rms {float(err.pow(2).mean().sqrt()):.2e}  "
           f"rel-to-max {float(err.max() / truth.abs().max()):.2e}")
+
+
+# ------------------------------------------------------------------------------------------
+# End to end: the oracle's render of the golden scenes with the velocity-MLP GEMMs replaced by each
+# scheme, against the reference's own outputs (tests/golden/*.npz) under the 1e-4 parity metric.
+# ------------------------------------------------------------------------------------------
+def end_to_end():
+    from oracle import nvfi_oracle as O
+    from tests.helpers import GOLDEN_SCENES, Golden
+
+    orig = O.mlp_forward
+
+    def make(scheme):
+        def mlp_forward(layers, x, act):
+            if len(layers) != 6 or layers[0][0].shape[1] != 28:      # only the velocity weight net
+                return orig(layers, x, act)
+            h = x
+            for i, (w, b) in enumerate(layers):
+                h = (gemm(h, w, scheme) + b.double()).float()
+                if i < len(layers) - 1:
+                    h = act(h)
+            return h
+        return mlp_forward
+
+    print("\nend to end (oracle render with emulated velocity GEMMs vs reference outputs; metric max |d| / max(|ref|, 1)):")
+    for name in GOLDEN_SCENES:
+        g = Golden(name)
+        sc = g.scene()
+        o, d = g.rays()
+        for case_name in ("eval1", "eval4"):      # one RK2 step / extrapolated (many steps)
+            case = g.case(case_name)
+            row = []
+            for scheme in ("fp32", "tf32", "tf32x3", "tf32+bf16", "fp16x3"):
+                O.mlp_forward = make(scheme) if scheme != "fp32" else orig
+                try:
+                    with torch.no_grad():
+                        out = O.render(sc, float(case["t"]), o, d, ray_chunk=g.ray_chunk,
+                                       white_bg=bool(g.cfg.dataset.white_background), training=False)
+                finally:
+                    O.mlp_forward = orig
+                errs = []
+                for k, i in (("rgb", 0), ("depth", 1), ("acc", 2), ("weights", 3)):
+                    ref = torch.from_numpy(case[k]).float()
+                    errs.append(float(((out[i] - ref).abs() / ref.abs().clamp_min(1.0)).max()))
+                row.append(f"{scheme} {max(errs):.1e}")
+            print(f"  {name:12s} {case_name} t={float(case['t']):.2f}: " + "  ".join(row))
+
+
+if __name__ == "__main__":
+    end_to_end()
