@@ -104,3 +104,26 @@ def test_camera_bundle_and_pixel_draw_match(ref):
     assert torch.equal(r_rays.ray_origins.expand_as(r_rays.ray_directions),
                        m_rays.ray_origins.expand_as(m_rays.ray_directions))
     assert torch.equal(r_tgt, m_tgt)
+
+
+def test_resolution_schedule_and_kwargs_match(ref):
+    """N_to_reso (utils/tensorf_utils.py:53-57) over the upsampling schedule of train_nvfi.py:99-105,
+    and the checkpoint kwargs of get_kwargs (train_nvfi.py:359-369)."""
+    from nvfi_b200 import models as M, synth
+    rcfg, mcfg = _cfg(ref, "bat")
+    aabb = synth.aabb_from_cfg(mcfg)
+    n_list = torch.round(torch.exp(torch.linspace(np.log(262144), np.log(8e6), 6))).long().tolist()
+    for n in n_list:
+        assert list(ref.utils.N_to_reso(n, aabb)) == list(M.N_to_reso(n, aabb)), n
+    grid = list(M.N_to_reso(262144, aabb))
+    nf = [mcfg.dataset.near, mcfg.dataset.far]
+    r = ref.models.NVFi(rcfg, "cpu", aabb, list(grid), nf)
+    m = M.NVFi(mcfg, "cpu", aabb, list(grid), nf)
+    rk, mk = r.nvfi.get_kwargs(), m.nvfi.get_kwargs()
+    assert sorted(rk) == sorted(mk)
+    for k in rk:
+        a, b = rk[k], mk[k]
+        if torch.is_tensor(a):
+            assert torch.equal(a.cpu().float(), torch.as_tensor(b).cpu().float()), k
+        elif isinstance(a, (int, float, str, bool, list, tuple)):
+            assert a == b or list(a) == list(b), k
