@@ -127,3 +127,40 @@ def test_resolution_schedule_and_kwargs_match(ref):
             assert torch.equal(a.cpu().float(), torch.as_tensor(b).cpu().float()), k
         elif isinstance(a, (int, float, str, bool, list, tuple)):
             assert a == b or list(a) == list(b), k
+
+
+def test_upsample_and_shrink_match(ref):
+    """upsample_volume_grid / shrink (models/tensorf_keyframe.py:328-376, 408-458) are torch-side
+    maintenance ops that REPLACE the parameters: same values, shapes, step size and aabb as the
+    reference, starting from the same state."""
+    from nvfi_b200 import models as M, synth
+    rcfg, mcfg = _cfg(ref, "bat")
+    aabb = synth.aabb_from_cfg(mcfg)
+    grid = [20, 18, 16]
+    nf = [mcfg.dataset.near, mcfg.dataset.far]
+    r = ref.models.NVFi(rcfg, "cpu", aabb, list(grid), nf)
+    m = M.NVFi(mcfg, "cpu", aabb, list(grid), nf)
+    sd = {k: torch.rand_like(v) for k, v in r.state_dict().items()}
+    r.load_state_dict(sd)
+    m.load_state_dict(sd)
+    K = int(mcfg.nvfi.num_keyframes)
+    r.nvfi.upsample_volume_grid([28, 26, 24], K)
+    m.nvfi.upsample_volume_grid([28, 26, 24], K)
+    rs, ms = r.state_dict(), m.state_dict()
+    assert sorted(rs) == sorted(ms)
+    for k in rs:
+        assert torch.equal(rs[k], ms[k]), k
+    assert r.nvfi.nSamples == m.nvfi.nSamples and float(r.nvfi.stepSize) == float(m.nvfi.stepSize)
+    new_aabb = torch.tensor([[-1.2, -1.0, -0.8], [1.1, 1.3, 0.9]])
+    # shrink reads alphaMask.gridSize (set by updateAlphaMask in the training loop): give both the same
+    # mask, on a grid that differs from gridSize so that the "correct aabb" branch runs
+    vol = (torch.rand(12, 13, 14) > 0.5).float()
+    r.nvfi.alphaMask = ref.models.AlphaGridMask("cpu", r.nvfi.aabb, vol.clone())
+    m.nvfi.alphaMask = M.AlphaGridMask("cpu", m.nvfi.aabb, vol.clone())
+    r.nvfi.shrink(new_aabb.clone())
+    m.nvfi.shrink(new_aabb.clone())
+    rs, ms = r.state_dict(), m.state_dict()
+    for k in rs:
+        assert torch.equal(rs[k], ms[k]), k
+    assert torch.equal(torch.as_tensor(r.nvfi.aabb).float().cpu(), torch.as_tensor(m.nvfi.aabb).float().cpu())
+    assert list(r.nvfi.gridSize) == list(m.nvfi.gridSize)
