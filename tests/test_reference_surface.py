@@ -164,3 +164,19 @@ def test_upsample_and_shrink_match(ref):
         assert torch.equal(rs[k], ms[k]), k
     assert torch.equal(torch.as_tensor(r.nvfi.aabb).float().cpu(), torch.as_tensor(m.nvfi.aabb).float().cpu())
     assert list(r.nvfi.gridSize) == list(m.nvfi.gridSize)
+
+
+@pytest.mark.parametrize("kw", [dict(n_layer=4, n_dim=128, input_dim=3, skips=[], mask_dim=3),
+                                dict(n_layer=8, n_dim=64, input_dim=3, skips=[4], mask_dim=5)])
+def test_mask_field_matches(ref, kw):
+    """MaskField (models/mask_field.py:34-83, as built at test_segm_render.py:75-80): same
+    parameters, same stand-alone forward."""
+    from nvfi_b200 import models as M
+    torch.manual_seed(3)
+    r = ref.models.MaskField(**kw)
+    m = M.MaskField(**kw)
+    assert sorted(r.state_dict()) == sorted(m.state_dict())
+    m.load_state_dict(r.state_dict())
+    x = torch.rand(257, 3) * 2 - 1
+    with torch.no_grad():
+        assert torch.allclose(r(x), m(x), atol=1e-7)
