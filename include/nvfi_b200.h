@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NVFI_ABI_VERSION 9
+#define NVFI_ABI_VERSION 10
 
 /* error codes */
 #define NVFI_OK 0
@@ -47,8 +47,10 @@ extern "C" {
 
 /* arithmetic of the velocity-MLP GEMMs (nvfi_set_mlp_mode) */
 #define NVFI_MLP_FP32_SIMT 0 /* FP32 FMA tile GEMM (verification path) */
-#define NVFI_MLP_TF32X3 1    /* tcgen05 TF32 tensor cores, 3-term split: FP32-grade (default) */
-#define NVFI_MLP_TF32 2      /* tcgen05 single TF32 pass: fastest, ~1e-3 relative */
+#define NVFI_MLP_TF32X3 1    /* tcgen05 TF32 tensor cores, 3-term split, activations in tensor memory */
+#define NVFI_MLP_TF32 2      /* tcgen05 single TF32 pass: ~1e-3 relative */
+#define NVFI_MLP_F16X3 3     /* tcgen05 FP16 tensor cores, 2-way operand split (hi + lo, 22 mantissa bits),
+                                3 MMAs per GEMM, operands in shared memory: FP32-grade (default) */
 
 #define NVFI_GATE_AABB 0 /* VelocityAABB,    models/velocity_field.py:21-33 */
 #define NVFI_GATE_SUR 1  /* VelocityAABBSur, models/velocity_field.py:36-51 */
@@ -73,6 +75,11 @@ typedef struct NvfiLinear {
   const float* ummaT;  /* the same kind of image of W^T (rows = input features: 128, or 32 for the
                           28-wide first layer; K = 128 outputs), for the input-gradient GEMMs of
                           the tensor-core backward pass; NULL when never differentiated */
+  const void* himg;    /* FP16-split tensor-core image produced by nvfi_pack_linear_h: per 64-wide K block
+                          the FP16 "hi" slab [rows][64] followed by the "lo" (residual) slab, K-major rows
+                          of 128 bytes with the 128-byte swizzle; rows = 128 (16 for the narrow head) */
+  const void* himgT;   /* the same kind of image of W^T (rows = input features: 128, or 32 for the 28-wide
+                          first layer; for the head: rows = 128 inputs, K = its outputs padded to 64) */
   int32_t in_dim, out_dim; /* logical sizes */
   int32_t k_pad, n_pad;    /* padded sizes: k_pad % 32 == 0, n_pad % 4 == 0 */
   int32_t umma_rows;       /* rows (N) of the image: 128 for hidden layers, 16 for a narrow head */
@@ -224,8 +231,8 @@ int nvfi_profile_enable(int on);
 int nvfi_profile_read(NvfiProfileEntry* out, int cap, int reset);
 
 /* Selects the arithmetic of the velocity-MLP GEMMs for subsequent calls (process-wide; the
- * default is NVFI_MLP_TF32X3, or the value of the environment variable NVFI_MLP_MODE =
- * simt | tf32x3 | tf32 at load).  Returns the previous mode, or NVFI_EINVAL. */
+ * default is NVFI_MLP_F16X3, or the value of the environment variable NVFI_MLP_MODE =
+ * simt | tf32x3 | tf32 | f16x3 at load).  Returns the previous mode, or NVFI_EINVAL. */
 int nvfi_set_mlp_mode(int mode);
 int nvfi_get_mlp_mode(void);
 
@@ -246,6 +253,12 @@ int nvfi_unpack_linear(const float* wt, const float* bias_in, float* w, float* b
  * (k_pad / 32) * 2 * n_rows * 32 floats. */
 int nvfi_pack_linear_umma(const float* w, float* dst, int out_dim, int in_dim, int n_rows, int k_pad,
                           void* stream);
+
+/* nn.Linear (out,in) -> FP16-split tensor-core image (see NvfiLinear.himg).  transposed == 0: rows = outputs
+ * (n_rows >= out_dim), K = inputs; transposed != 0: rows = inputs (n_rows >= in_dim), K = outputs.  K is padded
+ * to k_pad (a multiple of 64); dst holds (k_pad / 64) * n_rows * 256 bytes. */
+int nvfi_pack_linear_h(const float* w, void* dst, int out_dim, int in_dim, int n_rows, int k_pad,
+                       int transposed, void* stream);
 
 /* ---- rays ----------------------------------------------------------------------------
  * Camera.get_ray_bundle for selected pixels (models/camera.py:112-138):

@@ -12,12 +12,12 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnvfi_b200.so")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 VEL_LAYERS = 6
 MAX_MASK_LAYERS = 8
 
 ACT_SOFTPLUS, ACT_RELU, ACT_RELU_ABS = 0, 1, 2
-MLP_FP32_SIMT, MLP_TF32X3, MLP_TF32 = 0, 1, 2
+MLP_FP32_SIMT, MLP_TF32X3, MLP_TF32, MLP_F16X3 = 0, 1, 2, 3
 SHADING_MLP_PE, SHADING_SH = 0, 1
 GATE_AABB, GATE_SUR = 0, 1
 
@@ -29,7 +29,7 @@ P3 = C.c_void_p * 3
 
 class NvfiLinear(C.Structure):
     _fields_ = [("wt", C.c_void_p), ("bias", C.c_void_p), ("w_rows", C.c_void_p), ("umma", C.c_void_p),
-                ("ummaT", C.c_void_p), ("in_dim", C.c_int32), ("out_dim", C.c_int32), ("k_pad", C.c_int32), ("n_pad", C.c_int32),
+                ("ummaT", C.c_void_p), ("himg", C.c_void_p), ("himgT", C.c_void_p), ("in_dim", C.c_int32), ("out_dim", C.c_int32), ("k_pad", C.c_int32), ("n_pad", C.c_int32),
                 ("umma_rows", C.c_int32), ("ummaT_rows", C.c_int32)]
 
 
@@ -109,6 +109,7 @@ SIGNATURES = {
     "nvfi_set_mlp_mode": (_i, [_i]),
     "nvfi_get_mlp_mode": (_i, []),
     "nvfi_pack_linear_umma": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "nvfi_pack_linear_h": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "nvfi_pack_plane": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "nvfi_unpack_plane": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "nvfi_pack_linear": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -4,6 +4,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cuda_fp16.h>
+
 #include "nvfi_common.cuh"
 
 extern "C" int nvfi_launch_sample_advect(const NvfiField*, const NvfiRenderArgs*,
@@ -79,6 +81,25 @@ __global__ void k_pack_linear_umma(const float* __restrict__ w, float* __restric
   float* blk = dst + (size_t)kb * 2 * per_kb;
   blk[off] = hi;
   blk[per_kb + off] = lo;
+}
+
+// nn.Linear (out,in) -> FP16-split tensor-core image (NvfiLinear.himg / himgT): per 64-wide K block the
+// FP16 "hi" slab [n_rows][64] then the "lo" slab (v - hi, rounded to FP16), rows of 128 bytes whose
+// 16-byte chunks are XOR-swizzled with (row & 7) (canonical K-major SWIZZLE_128B layout).  Element
+// (row r, K index c) is w[r * sr + c * sc]: (sr, sc) = (in_dim, 1) for W, (1, in_dim) for W^T.
+__global__ void k_pack_linear_h(const float* __restrict__ w, unsigned char* __restrict__ dst, int r_valid,
+                                int c_valid, int sr, int sc, int n_rows, int k_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * k_pad) return;
+  const int r = i / k_pad, c = i - r * k_pad;
+  const float v = (r < r_valid && c < c_valid) ? w[(size_t)r * sr + (size_t)c * sc] : 0.f;
+  const __half hi = __float2half_rn(v);
+  const __half lo = __float2half_rn(v - __half2float(hi));
+  const size_t blk = (size_t)(c >> 6) * ((size_t)n_rows * 256);
+  const size_t off = (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)((((c & 63) >> 3) ^ (r & 7)) << 4) +
+                     (size_t)(c & 7) * 2;
+  *reinterpret_cast<__half*>(dst + blk + off) = hi;
+  *reinterpret_cast<__half*>(dst + blk + (size_t)n_rows * 128 + off) = lo;
 }
 
 // Camera.get_ray_bundle (models/camera.py:112-138), per selected pixel.
@@ -164,21 +185,35 @@ extern "C" int nvfi_pack_linear_umma(const float* w, float* dst, int out_dim, in
   return (int)cudaGetLastError();
 }
 
+extern "C" int nvfi_pack_linear_h(const float* w, void* dst, int out_dim, int in_dim, int n_rows, int k_pad,
+                                  int transposed, void* stream) {
+  const int r_valid = transposed ? in_dim : out_dim, c_valid = transposed ? out_dim : in_dim;
+  if (!w || !dst || out_dim <= 0 || in_dim <= 0 || n_rows < r_valid || k_pad < c_valid || (k_pad & 63) ||
+      (n_rows & 7))
+    return NVFI_EINVAL;
+  const int n = n_rows * k_pad;
+  NVFI_LAUNCH(k_pack_linear_h, (n + 255) / 256, 256, 0, (cudaStream_t)stream, w,
+              reinterpret_cast<unsigned char*>(dst), r_valid, c_valid, transposed ? 1 : in_dim,
+              transposed ? in_dim : 1, n_rows, k_pad);
+  return (int)cudaGetLastError();
+}
+
 static int g_mlp_mode = -1;
 extern "C" int nvfi_get_mlp_mode(void) {
   if (g_mlp_mode < 0) {
-    g_mlp_mode = NVFI_MLP_TF32X3;
+    g_mlp_mode = NVFI_MLP_F16X3;
     const char* e = getenv("NVFI_MLP_MODE");
     if (e) {
       if (!strcmp(e, "simt")) g_mlp_mode = NVFI_MLP_FP32_SIMT;
       else if (!strcmp(e, "tf32")) g_mlp_mode = NVFI_MLP_TF32;
       else if (!strcmp(e, "tf32x3")) g_mlp_mode = NVFI_MLP_TF32X3;
+      else if (!strcmp(e, "f16x3")) g_mlp_mode = NVFI_MLP_F16X3;
     }
   }
   return g_mlp_mode;
 }
 extern "C" int nvfi_set_mlp_mode(int mode) {
-  if (mode < NVFI_MLP_FP32_SIMT || mode > NVFI_MLP_TF32) return NVFI_EINVAL;
+  if (mode < NVFI_MLP_FP32_SIMT || mode > NVFI_MLP_F16X3) return NVFI_EINVAL;
   const int prev = nvfi_get_mlp_mode();
   g_mlp_mode = mode;
   return prev;

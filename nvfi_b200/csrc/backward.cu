@@ -954,6 +954,8 @@ using namespace nvfi;
 extern "C" int nvfi_get_mlp_mode(void);
 extern "C" int nvfi_launch_advect_bwd_tc(const NvfiField*, const NvfiRenderArgs*, const NvfiRenderBuffers*,
                                          const NvfiRenderGrads*, int, long long, int, int, cudaStream_t);
+extern "C" int nvfi_launch_advect_bwd_h(const NvfiField*, const NvfiRenderArgs*, const NvfiRenderBuffers*,
+                                        const NvfiRenderGrads*, int, long long, int, cudaStream_t);
 
 static int bwd_num_sms() {
   int dev = 0, sms = 148;
@@ -1051,7 +1053,9 @@ extern "C" int nvfi_render_backward(const NvfiField* F, const NvfiRenderArgs* A,
       if (!D->g_vel_w[l] || !D->g_vel_b[l] || (l < 5 && !F->vel_net[l].w_rows))
         return NVFI_EINVAL;
     const int mlp_mode = nvfi_get_mlp_mode();
-    if (mlp_mode != NVFI_MLP_FP32_SIMT)   // product path: tcgen05 tensor cores (backward_tc.cu)
+    if (mlp_mode == NVFI_MLP_F16X3)       // product path: FP16-split tcgen05 (backward_h.cu)
+      return nvfi_launch_advect_bwd_h(F, A, B, D, S, total, sms, st);
+    if (mlp_mode != NVFI_MLP_FP32_SIMT)   // round-1 path: 3xTF32 tcgen05 (backward_tc.cu)
       return nvfi_launch_advect_bwd_tc(F, A, B, D, S, total, sms, mlp_mode, st);
     const size_t smem = tile_smem + sizeof(AdvBwdTile);
     static bool attr = false;

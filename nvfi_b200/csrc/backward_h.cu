@@ -1,0 +1,664 @@
+// RK2 adjoint through the velocity MLP on the tensor cores with FP16-split operands (mlp_h.cuh): the
+// product path of nvfi_render_backward step 4 (backward_tc.cu = the round-1 3xTF32 path, k_advect_bwd in
+// backward.cu = the FP32 SIMT verification path).  Math: SURVEY.md Appendix E "RK2 step"; reference:
+// autograd of models/tensorf_keyframe.py:575-611 + models/velocity_field.py:54-98.
+//
+// Per tile of 128 advected samples and per RK2 step (reverse order) the kernel runs the program
+//     F1' (x0, no stash: gives the midpoint)  F2 (midpoint, stashed)  B2  F1 (x0, stashed)  B1
+// so that only ONE evaluation's stash is live (per CTA 608 KB: it stays in L2).  A stashed forward
+// evaluation leaves, per hidden layer l,
+//     A_l = silu(h_l)   as the 64 KB FP16 hi|lo tile image the next layer's MMAs read anyway, copied to
+//                       global memory by the TMA engine (cp.async.bulk, no thread instructions), and
+//     S_l = silu'(h_l)  FP32, unit-major, stored by the epilogue threads (coalesced),
+// so the backward pass evaluates no activation function at all.  With G_l = dL/dh_l (tile T_G) and
+// A_{l-1} (tile T_A, TMA-loaded from the stash), per layer l = 4..0:
+//     dX:  D0[m][k] = sum_n G_l[m][n] W_l[n][k]        A = T_G K-major,  B = W_l^T image (ring)
+//     dW:  D1[n][k] = sum_m G_l[m][n] A_{l-1}[m][k]    A = T_G MN-major, B = T_A MN-major  (same bytes!)
+//     db:  Db[n][.] = sum_m G_l[m][n] * 1              A = T_G MN-major, B = a constant block of ones
+//     G_{l-1} = D0 (.) S_{l-1} -> T_G (FP16 split);    D1 -> transposed into T_A -> ONE 64 KB
+//     cp.reduce.async.bulk (.add.f32) into the packed weight gradient; Db -> registers.
+// No operand is ever transposed by a thread: FP16 tiles can be read K-major and MN-major.
+// The head (128 -> 6) is two small MMAs against a [128][16] tile of the upstream gradient.
+//
+// FP16 range: the upstream gradient of a tile is scaled by a power of two so that its largest
+// component is in [8, 16) (12 binades of headroom for growth through the layers, 2^-29 of the tile
+// maximum as absolute resolution); every result is unscaled when it leaves the tensor cores.
+#include "backward_common.cuh"
+#include "mlp_h.cuh"
+
+namespace nvfi {
+namespace thb {
+
+constexpr int NT = th::kThreads;            // 512 worker threads (+ the issuer warp)
+constexpr uint32_t kStages = 2;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColD0 = 0;              // input-gradient accumulator (forward evaluations: 0 / 128)
+constexpr uint32_t kColD1 = 256;            // weight-gradient accumulator
+constexpr uint32_t kColDb = 384;            // column sums of G_l (16 columns)
+constexpr uint32_t kColDh = 400;            // head weight gradient (16 columns)
+
+// per-CTA global scratch (byte offsets)
+constexpr size_t kWsStashA = 0;
+constexpr size_t kWsStashS = th::kStashABytes;
+constexpr size_t kWsXsteps = kWsStashS + th::kStashSFloats * sizeof(float);
+constexpr size_t kWsBytes = kWsXsteps + (size_t)MAX_RK2_STEPS * 3 * NVFI_TM * sizeof(float);
+static_assert(kWsBytes <= (size_t)WS_CTA_F * sizeof(float), "per-CTA workspace of k_advect_bwd_h exceeds WS_CTA_F");
+
+struct BwdTile {
+  alignas(128) unsigned char gw_hi[4096];   // upstream gradient of the head, [128 samples][16] FP16 (no swizzle)
+  alignas(128) unsigned char gw_lo[4096];
+  alignas(128) unsigned char ones[512];     // [16][16] FP16 1.0
+  float x0[3][NVFI_TM];
+  float xm[3][NVFI_TM];
+  float gbar[3][NVFI_TM];
+  float gm[3][NVFI_TM];
+  float w0[6][NVFI_TM];
+  float w1[6][NVFI_TM];
+  float gout[6][NVFI_TM];   // in: dL/d(basis weights); out (rows 0..2): dL/d(x, y, z) of the eval input
+  float tvec[NVFI_TM];
+  unsigned char gate0[NVFI_TM], gate1[NVFI_TM], reverted[NVFI_TM];
+  int gidx[NVFI_TM];
+  int q_idx[NVFI_TM + NT];
+  int warp_cnt[2][NT / 32];
+  int batch;
+  unsigned gmax;            // bits of the largest |upstream gradient| of the tile
+  th::Issuer iss;           // weight-ring state of the issuer warp between calls
+};
+
+__device__ __forceinline__ float ldcg_now(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void red_add(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
+
+// ---- backward through one weight-net evaluation -------------------------------------------
+// In: T.gout[n][m] = dL/d(basis weights); tile tA holds A_4 of the stashed evaluation that has just run;
+// stash_a / stash_s = that evaluation's stash; (xs, ys, zs)[m] = its input.  Out: T.gout[0..2][m] =
+// dL/d(x, y, z) through the network input; weight gradients added to the packed gradient buffers, bias
+// and head gradients to the register accumulators.  Whole CTA (13 block barriers).
+__device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint32_t tA, uint32_t tG,
+                           const NvfiRenderGrads& D, const unsigned char* __restrict__ stash_a,
+                           const float* __restrict__ stash_s, const float* xs, const float* ys, const float* zs,
+                           uint32_t& dphase, uint32_t& wphase, uint32_t& aphase, float (&acc_head)[6],
+                           float (&acc_bias)[6]) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t gw_hi = tc::smem_u32(T.gw_hi), gw_lo = tc::smem_u32(T.gw_lo), ones = tc::smem_u32(T.ones);
+
+  // ---- scale of the tile: largest |dL/dw| -> [8, 16)
+  if (tid < NVFI_TM) {
+    float mx = 0.f;
+#pragma unroll
+    for (int n = 0; n < 6; ++n) mx = fmaxf(mx, fabsf(T.gout[n][tid]));
+    const unsigned b = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+    if (lane == 0 && b) atomicMax(&T.gmax, b);
+  }
+  __syncthreads();   // (S0)
+  float scale = 1.f, inv_scale = 1.f;
+  {
+    const unsigned b = T.gmax;
+    if (b) {
+      unsigned ex = b >> 23;
+      ex = ex < 30u ? 30u : (ex > 250u ? 250u : ex);
+      scale = __uint_as_float((257u - ex) << 23);
+      inv_scale = __uint_as_float((ex - 3u) << 23);
+    }
+  }
+
+  if (warp == th::kIssuerWarp) {   // ==================================================== issuer warp
+    th::Issuer is = is_shared;
+    th::ring_top_up(c, is, false);
+    __syncthreads();   // (A) upstream-gradient tile written
+    tc::tc_fence_after();
+    const uint32_t tb = is.tb;
+    const uint32_t id128 = th::idesc_f16(128), id32 = th::idesc_f16(32);
+    const uint32_t hs = th::kDescHiSw128;
+    if (tc::elect_one()) th::bulk_wait0();   // the stash copies of the forward evaluation have landed
+    __syncwarp();
+    // ---- head, dX: D0[m][u] = sum_n gw[m][n] W5[n][u]   (K = 16: one step)
+    {
+      const uint32_t st = th::ring_acquire(c, is);
+      if (tc::elect_one()) {
+        const uint32_t a_h = th::desc_lo(gw_hi, 128), a_l = th::desc_lo(gw_lo, 128);
+        const uint32_t b_h = th::desc_lo(st), b_l = th::desc_lo(st + 128u * 128u);
+        th::mma_f16_ss(tb + kColD0, a_h, th::kDescHiSmallK, b_h, hs, id128, 0u);
+        th::mma_f16_ss(tb + kColD0, a_l, th::kDescHiSmallK, b_h, hs, id128, 1u);
+        th::mma_f16_ss(tb + kColD0, a_h, th::kDescHiSmallK, b_l, hs, id128, 1u);
+        tc::tc_commit(&c.empty[is.c_stage]);
+        tc::tc_commit(&c.dbar);
+      }
+      __syncwarp();
+      th::ring_advance(is);
+    }
+    // ---- head, dW: Dh[k][n] = sum_m A_4[m][k] gw[m][n]   (A = tA MN-major, B = gw MN-major, N = 16)
+    if (tc::elect_one()) {
+      const uint32_t idh = th::idesc_f16(16, 1, 1);
+#pragma unroll 2
+      for (uint32_t ks = 0; ks < 8; ++ks) {
+        const uint32_t a_h = th::desc_lo(tA + ks * 2048u, 16384), a_l = th::desc_lo(tA + th::kLoOff + ks * 2048u, 16384);
+        const uint32_t b_h = th::desc_lo(gw_hi + ks * 512u, 256), b_l = th::desc_lo(gw_lo + ks * 512u, 256);
+        th::mma_f16_ss(tb + kColDh, a_h, hs, b_h, th::kDescHiSmallMN, idh, ks ? 1u : 0u);
+        th::mma_f16_ss(tb + kColDh, a_l, hs, b_h, th::kDescHiSmallMN, idh, 1u);
+        th::mma_f16_ss(tb + kColDh, a_h, hs, b_l, th::kDescHiSmallMN, idh, 1u);
+      }
+      tc::tc_commit(&c.wbar);
+    }
+    __syncwarp();
+    tc::mbar_wait(&c.wbar, wphase & 1);   // A_4 consumed: tile tA is free
+    if (tc::elect_one()) {
+      tc::mbar_expect_tx(&c.abar, th::kTileBytes);
+      tc::bulk_g2s_u32(tA, stash_a + 32768 + (size_t)3 * th::kTileBytes, th::kTileBytes, &c.abar);   // A_3
+    }
+    __syncwarp();
+    th::ring_top_up(c, is, false);
+    __syncthreads();   // (B) G_4 in tile tG
+    tc::tc_fence_after();
+    // dX of layer l: D0[m][k] = sum_n G_l[m][n] W_l[n][k]
+    auto issue_dx = [&](int l) {
+      const uint32_t nx = (l == 0) ? 32u : 128u;
+      const uint32_t idx = (l == 0) ? id32 : id128;
+#pragma unroll 1
+      for (uint32_t kb = 0; kb < 2; ++kb) {
+        const uint32_t st = th::ring_acquire(c, is);
+        if (tc::elect_one()) {
+#pragma unroll
+          for (uint32_t ks = 0; ks < 4; ++ks) {
+            const uint32_t a_h = th::desc_lo(tG + kb * th::kSlab) + ks * 2u;
+            const uint32_t a_l = th::desc_lo(tG + th::kLoOff + kb * th::kSlab) + ks * 2u;
+            const uint32_t b_h = th::desc_lo(st) + ks * 2u, b_l = th::desc_lo(st + nx * 128u) + ks * 2u;
+            th::mma_f16_ss(tb + kColD0, a_h, hs, b_h, hs, idx, (kb | ks) ? 1u : 0u);
+            th::mma_f16_ss(tb + kColD0, a_l, hs, b_h, hs, idx, 1u);
+            th::mma_f16_ss(tb + kColD0, a_h, hs, b_l, hs, idx, 1u);
+          }
+          tc::tc_commit(&c.empty[is.c_stage]);
+          if (kb == 1) tc::tc_commit(&c.dbar);
+        }
+        __syncwarp();
+        th::ring_advance(is);
+        th::ring_top_up(c, is, false);
+      }
+    };
+    issue_dx(4);
+#pragma unroll 1
+    for (int l = 4; l >= 0; --l) {
+      tc::mbar_wait(&c.abar, aphase & 1);   // A_{l-1} (l = 0: the encoding) is in tile tA
+      ++aphase;
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        // dW: D1[n][k] = sum_m G_l[m][n] A_{l-1}[m][k]; db: Db[n][.] = sum_m G_l[m][n]
+        const uint32_t idw = th::idesc_f16(l == 0 ? 32 : 128, 1, 1), idb = th::idesc_f16(16, 1, 0);
+        const uint32_t o_h = th::desc_lo(ones, 128);
+#pragma unroll 2
+        for (uint32_t ks = 0; ks < 8; ++ks) {
+          const uint32_t g_h = th::desc_lo(tG + ks * 2048u, 16384), g_l = th::desc_lo(tG + th::kLoOff + ks * 2048u, 16384);
+          const uint32_t a_h = th::desc_lo(tA + ks * 2048u, 16384), a_l = th::desc_lo(tA + th::kLoOff + ks * 2048u, 16384);
+          th::mma_f16_ss(tb + kColD1, g_h, hs, a_h, hs, idw, ks ? 1u : 0u);
+          th::mma_f16_ss(tb + kColD1, g_l, hs, a_h, hs, idw, 1u);
+          th::mma_f16_ss(tb + kColD1, g_h, hs, a_l, hs, idw, 1u);
+          th::mma_f16_ss(tb + kColDb, g_h, hs, o_h, th::kDescHiSmallK, idb, ks ? 1u : 0u);
+          th::mma_f16_ss(tb + kColDb, g_l, hs, o_h, th::kDescHiSmallK, idb, 1u);
+        }
+        tc::tc_commit(&c.wbar);
+      }
+      __syncwarp();
+      __syncthreads();   // (C1) G_{l-1} in tile tG
+      tc::tc_fence_after();
+      if (l > 0) issue_dx(l - 1);
+      __syncthreads();   // (C2) D1 staged (transposed) in tile tA
+      if (tc::elect_one()) {
+        th::bulk_reduce_add_f32(D.g_vel_w[l], tA, l == 0 ? 16384u : 65536u);
+        th::bulk_commit();
+        if (l > 0) {
+          th::bulk_wait_read0();   // the staging rows have been read: the tile may be overwritten
+          if (l >= 2) {
+            tc::mbar_expect_tx(&c.abar, th::kTileBytes);
+            tc::bulk_g2s_u32(tA, stash_a + 32768 + (size_t)(l - 2) * th::kTileBytes, th::kTileBytes, &c.abar);
+          } else {   // the encoding: columns 0..31 of slab 0, hi and lo
+            tc::mbar_expect_tx(&c.abar, 2u * th::kSlab);
+            tc::bulk_g2s_u32(tA, stash_a, th::kSlab, &c.abar);
+            tc::bulk_g2s_u32(tA + th::kLoOff, stash_a + th::kSlab, th::kSlab, &c.abar);
+          }
+        } else {
+          th::bulk_wait_read0();
+        }
+      }
+      __syncwarp();
+    }
+    dphase += 6;
+    wphase += 6;
+    is_shared = is;
+    return;
+  }
+
+  // ================================================================================ worker warps
+  const int q = warp & 3, h = warp >> 2;
+  const int m = q * 32 + lane;                 // sample (sample-major steps) / unit n (flush steps) of this thread
+  const uint32_t tb = c.tmem_base;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  const uint32_t row_u32 = tG + (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);
+  const uint32_t x7 = (uint32_t)(m & 7);
+
+  if (tid < NVFI_TM) {   // upstream gradient of the head -> [128][16] FP16 tile (columns 6..15 zero)
+    float v[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) v[n] = (n < 6) ? T.gout[n][m] * scale : 0.f;
+    uint4 hi, lo;
+    th::split8(v, hi, lo);
+    const uint32_t off = (uint32_t)((m >> 3) * 256 + (m & 7) * 16);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    th::st_shared_v4(gw_hi + off, hi);
+    th::st_shared_v4(gw_hi + off + 128u, z);
+    th::st_shared_v4(gw_lo + off, lo);
+    th::st_shared_v4(gw_lo + off + 128u, z);
+    th::fence_async_smem();
+  }
+  if (warp < 6)     // db5[n] = sum_m gout[n][m]: warp n, each lane 4 samples (reduced at kernel end)
+    acc_bias[5] += T.gout[warp][lane] + T.gout[warp][lane + 32] + T.gout[warp][lane + 64] + T.gout[warp][lane + 96];
+  tc::tc_fence_before();
+  __syncthreads();   // (A)
+  if (tid == 0) T.gmax = 0u;
+
+#pragma unroll 1
+  for (int L = 5; L >= 0; --L) {
+    // ---- S_{L-1}[unit][sample] of this thread's 32 columns: coalesced loads, issued before the wait
+    float sv[4][8];
+    if (L > 0) {
+      const float* sp = stash_s + ((size_t)(L - 1) * NVFI_TM + h * 8) * NVFI_TM + m;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sv[g][i] = ldcg_now(sp + (size_t)(g * 32 + i) * NVFI_TM);
+    }
+    tc::mbar_wait(&c.dbar, dphase & 1);   // D0 = dX(L)
+    ++dphase;
+    tc::tc_fence_after();
+    uint4 ghi[4], glo[4];
+    if (L > 0) {
+      // G_{L-1} = D0 (.) S_{L-1}, FP16 split, held in registers until tile tG is free
+      const uint32_t dcol = tb + lane_base + kColD0 + (uint32_t)(h * 8);
+      uint32_t raw[4][8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tc::tmem_ld8_nowait(dcol + 32u * g, raw[g]);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[g][i]) * sv[g][i];
+        th::split8(v, ghi[g], glo[g]);
+      }
+    } else if (h == 0) {
+      // dL/d(encoding) -> dL/d(x, y, z)  (encoder tangents)
+      float ge[32];
+      tc::tmem_ld32(tb + lane_base + kColD0, ge);
+      const float qv[3] = {xs[m], ys[m], zs[m]};
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        float s1, c1, s2, c2, s4, c4;
+        tc::sincos_bounded(qv[i], s1, c1);
+        tc::sincos_bounded(qv[i] * 2.f, s2, c2);
+        tc::sincos_bounded(qv[i] * 4.f, s4, c4);
+        T.gout[i][m] = inv_scale * (ge[i] + ge[4 + i] * c1 - ge[8 + i] * s1 +
+                                    2.f * (ge[12 + i] * c2 - ge[16 + i] * s2) +
+                                    4.f * (ge[20 + i] * c4 - ge[24 + i] * s4));
+      }
+    }
+    tc::mbar_wait(&c.wbar, wphase & 1);   // dW(L) and db(L) done: tiles tG and tA are free
+    ++wphase;
+    tc::tc_fence_after();
+    if (L > 0) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t a = row_u32 + (uint32_t)(g >> 1) * th::kSlab + ((((uint32_t)(4 * g + h) & 7u) ^ x7) << 4);
+        th::st_shared_v4(a, ghi[g]);
+        th::st_shared_v4(a + th::kLoOff, glo[g]);
+      }
+      th::fence_async_smem();
+    }
+    tc::tc_fence_before();
+    __syncthreads();   // (B) for the head, (C1) for the hidden layers
+    if (L == 5) {
+      if (h == 0) {   // dW5^T[k][n]: unit k = m
+        uint32_t r[8];
+        tc::tmem_ld8_nowait(tb + lane_base + kColDh, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int n = 0; n < 6; ++n) acc_head[n] = fmaf(__uint_as_float(r[n]), inv_scale, acc_head[n]);
+      }
+      continue;
+    }
+    // ---- D1[n][k] -> staging rows stage[k][n] in tile tA (this thread: n = m, k = 32 h + i); the issuer
+    //      adds the block to the packed gradient with one bulk reduction
+    if (L > 0 || h == 0) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float dv[16];
+        tc::tmem_ld16(tb + lane_base + kColD1 + (uint32_t)(h * 32 + half * 16), dv);
+        const uint32_t sa = tA + (uint32_t)(((h * 32 + half * 16) * NVFI_TM + m) * 4);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa + (uint32_t)(i * NVFI_TM * 4)), "f"(dv[i] * inv_scale) : "memory");
+      }
+    }
+    if (h == 0) {
+      uint32_t r;
+      tmem_ld1(tb + lane_base + kColDb, r);
+      tc::tmem_ld_wait();
+      acc_bias[L] = fmaf(__uint_as_float(r), inv_scale, acc_bias[L]);
+    }
+    th::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();   // (C2)
+  }
+}
+
+// v = basis(w, x): dL/dw and the explicit dL/dx from dL/dv (as in backward.cu)
+__device__ __forceinline__ void basis_bwd(const float w[6], float x, float y, float z, const float gv[3],
+                                          float gw[6], float gxe[3]) {
+  gw[0] = gv[0];
+  gw[1] = gv[1];
+  gw[2] = gv[2];
+  gw[3] = gv[1] * z - gv[2] * y;
+  gw[4] = -gv[0] * z + gv[2] * x;
+  gw[5] = gv[0] * y - gv[1] * x;
+  gxe[0] = -w[5] * gv[1] + w[4] * gv[2];
+  gxe[1] = w[5] * gv[0] - w[3] * gv[2];
+  gxe[2] = -w[4] * gv[0] + w[3] * gv[1];
+}
+
+// 17 warps are allocated as 20: 96 registers per thread is the cap.
+__global__ void __launch_bounds__(th::kLaunchThreads, 1)
+    k_advect_bwd_h(const __grid_constant__ NvfiField F, const NvfiRenderArgs A, const NvfiRenderBuffers B,
+                   const NvfiRenderGrads D, int S, long long total, int n_batches, int subs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* p = smem_raw;
+  {
+    const uint32_t a = tc::smem_u32(p);
+    p += (1024u - (a & 1023u)) & 1023u;
+  }
+  const uint32_t tA = tc::smem_u32(p);                    // activation tile
+  const uint32_t tG = tA + th::kTileBytes;                // gradient tile
+  const uint32_t ring = tG + th::kTileBytes;              // kStages x 32 KB
+  th::Ctl1& ctl = *reinterpret_cast<th::Ctl1*>(p + 2 * th::kTileBytes + kStages * th::kStageBytes);
+  BwdTile& T = *reinterpret_cast<BwdTile*>(reinterpret_cast<unsigned char*>(&ctl) + ((sizeof(th::Ctl1) + 127) & ~(size_t)127));
+  unsigned char* ws = reinterpret_cast<unsigned char*>(D.workspace) + (size_t)blockIdx.x * WS_CTA_F * sizeof(float);
+  unsigned char* stash_a = ws + kWsStashA;
+  float* stash_s = reinterpret_cast<float*>(ws + kWsStashS);
+  float* xsteps = reinterpret_cast<float*>(ws + kWsXsteps);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // uniform RK2 schedule of this render call (models/tensorf_keyframe.py:577-609)
+  float sched_dt[MAX_RK2_STEPS], sched_t[MAX_RK2_STEPS];
+  int n_steps = 0;
+  {
+    float off = __fsub_rn(A.t, A.base_time), tc_ = A.t;
+    while (fabsf(off) > 0.f && n_steps < MAX_RK2_STEPS) {
+      float dt = fminf(fabsf(off), F.dt_max);
+      dt = (off > 0.f) ? dt : -dt;
+      sched_dt[n_steps] = dt;
+      sched_t[n_steps] = tc_;
+      off = __fsub_rn(off, dt);
+      tc_ = __fsub_rn(tc_, dt);
+      ++n_steps;
+    }
+  }
+
+  th::setup(ctl, F.vel_net, nullptr, kTmemCols);
+  if (tid == 0) {   // weight segments in the order one tile consumes them
+    int n = 0;
+    for (int k = 0; k + 1 < n_steps; ++k) {
+      ctl.prog[n++] = th::SEG_FWD0;
+      ctl.prog[n++] = th::SEG_FWD0;
+    }
+    for (int k = 0; k < n_steps; ++k) {   // F1', F2 (stashed), B2, F1 (stashed), B1
+      ctl.prog[n++] = th::SEG_FWD0;
+      ctl.prog[n++] = th::SEG_FWD0;
+      ctl.prog[n++] = th::SEG_BWD0;
+      ctl.prog[n++] = th::SEG_FWD0;
+      ctl.prog[n++] = th::SEG_BWD0;
+    }
+    ctl.prog_len = (uint32_t)n;
+    T.gmax = 0u;
+  }
+  for (int i = tid; i < 256; i += blockDim.x) reinterpret_cast<unsigned short*>(T.ones)[i] = 0x3C00u;   // FP16 1.0
+  th::fence_async_smem();
+  __syncthreads();
+  if (warp == th::kIssuerWarp) T.iss.init(ctl, ring, kStages);
+  __syncthreads();
+  uint32_t dphase = 0, kphase = 0, wphase = 0, aphase = 0;
+
+  int sub = subs;
+  long long batch_base = 0;
+  bool exhausted = false;
+  int qc = 0, par = 0;
+  unsigned long long n_done = 0;
+  // per-thread partial sums of the head-layer weight gradient (unit k = tid < 128) and of the bias
+  // gradients (unit n = tid < 128; the head's: warps 0..5), carried in registers across all tiles
+  float acc_head[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, acc_bias[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+
+  // One tile = a short program of evaluations.  There is exactly ONE call site of the forward tile
+  // evaluation and one of the backward tile evaluation (instruction-cache footprint); the small
+  // per-sample glue around them is selected by `kind`.
+  enum { K_FWD_A = 0, K_FWD_B, K_REV_A0, K_REV_B, K_BWD2, K_REV_A, K_BWD1 };
+  const int n_ops = 2 * (n_steps - 1) + 5 * n_steps;
+
+  for (;;) {
+    while (qc < NVFI_TM && !exhausted) {
+      if (sub == subs) {
+        if (tid == 0) T.batch = atomicAdd(&B.counters[3], 1);
+        __syncthreads();
+        const int b = T.batch;
+        __syncthreads();
+        if (b >= n_batches) {
+          exhausted = true;
+          break;
+        }
+        batch_base = (long long)b * ((long long)subs * NT);
+        sub = 0;
+      }
+      const long long idx = batch_base + (long long)sub * NT + tid;
+      ++sub;
+      bool push = false;
+      if (tid < NT && idx < total && B.valid[idx]) {
+        const float g0 = D.g_x_adv[idx * 3], g1 = D.g_x_adv[idx * 3 + 1], g2 = D.g_x_adv[idx * 3 + 2];
+        push = (g0 != 0.f) | (g1 != 0.f) | (g2 != 0.f);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, push);
+      if (lane == 0 && warp < NT / 32) T.warp_cnt[par][warp] = __popc(bal);
+      const int tot = __syncthreads_count(push);
+      if (push) {
+        int pos = qc + __popc(bal & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) pos += T.warp_cnt[par][w];
+        T.q_idx[pos] = (int)idx;
+      }
+      qc += tot;
+      par ^= 1;
+    }
+    if (qc == 0) break;
+    __syncthreads();
+    const int n = min(NVFI_TM, qc);
+    const int start = qc - n;
+    qc = start;
+    n_done += n;
+    // ---- load the tile: start position (sampler recompute) and upstream gradient
+    if (tid < NVFI_TM) {
+      const bool live = tid < n;
+      const long long gi = live ? T.q_idx[start + tid] : 0;
+      T.gidx[tid] = (int)gi;
+      float xn[3] = {0.f, 0.f, 0.f};
+      if (live) {
+        const long long ray = gi / S;
+        const int s = (int)(gi - ray * S);
+        const float o[3] = {__ldg(A.rays_o + ray * 3), __ldg(A.rays_o + ray * 3 + 1),
+                            __ldg(A.rays_o + ray * 3 + 2)};
+        const float d[3] = {__ldg(A.rays_d + ray * 3), __ldg(A.rays_d + ray * 3 + 1),
+                            __ldg(A.rays_d + ray * 3 + 2)};
+        const bool inside = B.chunk_inside[ray / A.ray_chunk] != 0;
+        const float tmin = ray_tmin(F, o, d, inside);
+        const bool train = A.jitter != nullptr;
+        const float u = train ? __ldg(A.jitter + ray) : 0.f;
+        sample_point(F, o, d, sample_z(tmin, F.step_size, s, u, train), xn);
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        T.x0[a][tid] = xn[a];
+        T.gbar[a][tid] = live ? D.g_x_adv[gi * 3 + a] : 0.f;
+      }
+    }
+    __syncthreads();
+
+#pragma unroll 1
+    for (int op = 0; op < n_ops; ++op) {
+      int k, kind;
+      if (op < 2 * (n_steps - 1)) {   // forward sweep over all but the last step
+        k = op >> 1;
+        kind = K_FWD_A + (op & 1);
+      } else {                        // reverse sweep
+        const int r = op - 2 * (n_steps - 1);
+        k = n_steps - 1 - r / 5;
+        kind = K_REV_A0 + r % 5;
+      }
+      const float dt = sched_dt[k], tcur = sched_t[k], hdt = 0.5f * dt;
+      const float tmid = __fsub_rn(tcur, hdt);
+      const bool at_mid = (kind == K_FWD_B || kind == K_REV_B || kind == K_BWD2);
+      // ---- glue before the evaluation
+      if (tid < NVFI_TM) {
+        if (kind == K_FWD_A) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) xsteps[(k * 3 + a) * NVFI_TM + tid] = T.x0[a][tid];
+        }
+        if (kind == K_REV_A0 && k < n_steps - 1) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) T.x0[a][tid] = xsteps[(k * 3 + a) * NVFI_TM + tid];
+        }
+        if (kind != K_BWD2 && kind != K_BWD1) T.tvec[tid] = at_mid ? tmid : tcur;
+      }
+      __syncthreads();
+      const float* xs = at_mid ? T.xm[0] : T.x0[0];
+      const float* ys = at_mid ? T.xm[1] : T.x0[1];
+      const float* zs = at_mid ? T.xm[2] : T.x0[2];
+      if (kind == K_BWD2 || kind == K_BWD1) {
+        bwd_eval_h(ctl, T.iss, T, tA, tG, D, stash_a, stash_s, xs, ys, zs, dphase, wphase, aphase, acc_head,
+                   acc_bias);
+      } else {
+        float* wout = at_mid ? &T.w1[0][0] : &T.w0[0][0];
+        const bool st = (kind == K_REV_B || kind == K_REV_A);
+        th::vel_net_tile_h<ACT_SILU>(ctl, T.iss, 0, wout, xs, ys, zs, T.tvec, tA, dphase, kphase,
+                                     st ? stash_a : nullptr, st ? stash_s : nullptr);
+      }
+      // ---- glue after the evaluation
+      if (tid < NVFI_TM) {
+        const int m = tid;
+        if (kind == K_FWD_A || kind == K_REV_A0) {   // midpoint m = x0 - dt/2 v0(x0)
+          const float x = T.x0[0][m], y = T.x0[1][m], z = T.x0[2][m];
+          float v[3] = {0.f, 0.f, 0.f};
+          const bool out0 = gate_outside(F, x, y, z);
+          T.gate0[m] = out0;
+          if (!out0) {
+            const float w[6] = {T.w0[0][m], T.w0[1][m], T.w0[2][m], T.w0[3][m], T.w0[4][m], T.w0[5][m]};
+            basis_velocity(w, x, y, z, v);
+          }
+          T.xm[0][m] = __fsub_rn(x, __fmul_rn(hdt, v[0]));
+          T.xm[1][m] = __fsub_rn(y, __fmul_rn(hdt, v[1]));
+          T.xm[2][m] = __fsub_rn(z, __fmul_rn(hdt, v[2]));
+        } else if (kind == K_FWD_B || kind == K_REV_B) {   // x1 = x0 - dt v1(m)
+          const float xm = T.xm[0][m], ym = T.xm[1][m], zm = T.xm[2][m];
+          const bool out1 = gate_outside(F, xm, ym, zm);
+          const float w[6] = {T.w1[0][m], T.w1[1][m], T.w1[2][m], T.w1[3][m], T.w1[4][m], T.w1[5][m]};
+          float v[3] = {0.f, 0.f, 0.f};
+          if (!out1) basis_velocity(w, xm, ym, zm, v);
+          const float x = T.x0[0][m], y = T.x0[1][m], z = T.x0[2][m];
+          float nx = __fsub_rn(x, __fmul_rn(dt, v[0]));
+          float ny = __fsub_rn(y, __fmul_rn(dt, v[1]));
+          float nz = __fsub_rn(z, __fmul_rn(dt, v[2]));
+          const bool rev = (F.vel_gate == NVFI_GATE_SUR) && gate_outside(F, nx, ny, nz);
+          if (kind == K_FWD_B) {      // advance to the next step
+            T.x0[0][m] = rev ? x : nx;
+            T.x0[1][m] = rev ? y : ny;
+            T.x0[2][m] = rev ? z : nz;
+          } else {                    // adjoint of x1 = x0 - dt v1(m)
+            T.gate1[m] = out1;
+            T.reverted[m] = rev;
+            float gw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gxe[3] = {0.f, 0.f, 0.f};
+            if (!rev && !out1) {
+              const float gv[3] = {-dt * T.gbar[0][m], -dt * T.gbar[1][m], -dt * T.gbar[2][m]};
+              basis_bwd(w, xm, ym, zm, gv, gw, gxe);
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) T.gout[i][m] = gw[i];
+            T.gm[0][m] = gxe[0];
+            T.gm[1][m] = gxe[1];
+            T.gm[2][m] = gxe[2];
+          }
+        } else if (kind == K_BWD2) {   // adjoint of m = x0 - dt/2 v0(x0)
+          float gmv[3];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) gmv[a] = T.gm[a][m] + T.gout[a][m];
+          float gx0[3] = {T.gbar[0][m] + gmv[0], T.gbar[1][m] + gmv[1], T.gbar[2][m] + gmv[2]};
+          float gw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (!T.gate0[m]) {
+            const float w[6] = {T.w0[0][m], T.w0[1][m], T.w0[2][m], T.w0[3][m], T.w0[4][m], T.w0[5][m]};
+            const float gv[3] = {-hdt * gmv[0], -hdt * gmv[1], -hdt * gmv[2]};
+            float gxe[3];
+            basis_bwd(w, T.x0[0][m], T.x0[1][m], T.x0[2][m], gv, gw, gxe);
+            gx0[0] += gxe[0];
+            gx0[1] += gxe[1];
+            gx0[2] += gxe[2];
+          }
+          T.gbar[0][m] = gx0[0];
+          T.gbar[1][m] = gx0[1];
+          T.gbar[2][m] = gx0[2];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) T.gout[i][m] = gw[i];
+        } else if (kind == K_BWD1) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) T.gbar[a][m] += T.gout[a][m];
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid < NVFI_TM) {
+#pragma unroll
+    for (int n2 = 0; n2 < 6; ++n2) red_add(D.g_vel_w[5] + tid * 8 + n2, acc_head[n2]);
+#pragma unroll
+    for (int l = 0; l < 5; ++l) red_add(D.g_vel_b[l] + tid, acc_bias[l]);
+  }
+  if (warp < 6) {
+    const float s5 = warp_sum(acc_bias[5]);
+    if (lane == 0) red_add(D.g_vel_b[5] + warp, s5);
+  }
+  if (warp == th::kIssuerWarp && tc::elect_one()) th::bulk_wait0();   // outstanding bulk reductions
+  th::teardown(ctl, T.iss, kTmemCols);
+  if (tid == 0 && n_done)
+    atomicAdd(reinterpret_cast<unsigned long long*>(B.counters + 10), n_done);
+}
+
+}  // namespace thb
+}  // namespace nvfi
+
+using namespace nvfi;
+
+extern "C" int nvfi_launch_advect_bwd_h(const NvfiField* F, const NvfiRenderArgs* A, const NvfiRenderBuffers* B,
+                                        const NvfiRenderGrads* D, int S, long long total, int sms, cudaStream_t st) {
+  for (int l = 0; l < NVFI_VEL_LAYERS; ++l)
+    if (!F->vel_net[l].himg || !F->vel_net[l].himgT) return NVFI_EINVAL;
+  if (F->vel_net[5].n_pad != 8) return NVFI_EUNSUPPORTED;
+  const size_t smem = 1024 + 2 * (size_t)th::kTileBytes + (size_t)thb::kStages * th::kStageBytes +
+                      ((sizeof(th::Ctl1) + 127) & ~(size_t)127) + sizeof(thb::BwdTile);
+  static size_t cached = 0;
+  if (smem > cached) {
+    NVFI_CUDA_OK(cudaFuncSetAttribute(thb::k_advect_bwd_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cached = smem;
+  }
+  const int subs = grab_subs(total, thb::NT, sms);
+  const int per_batch = subs * thb::NT;
+  const int n_batches = (int)((total + per_batch - 1) / per_batch);
+  const int grid = n_batches < sms ? n_batches : sms;
+  NVFI_LAUNCH(thb::k_advect_bwd_h, grid, th::kLaunchThreads, smem, st, *F, *A, *B, *D, S, total, n_batches, subs);
+  return (int)cudaGetLastError();
+}

@@ -14,6 +14,7 @@
 // shared-memory queue.  Whenever 128 entries are queued they are advected as one tile
 // by the FP32 tile-GEMM MLP (nvfi_common.cuh); leftovers carry over, so no tile is
 // padded except the very last one of a CTA.
+#include "mlp_h.cuh"
 #include "mlp_tc.cuh"
 #include "nvfi_common.cuh"
 
@@ -73,6 +74,34 @@ struct TcMlp {
   __device__ void eval(int which, float* outS, const float* xs, const float* ys, const float* zs,
                        const float* ts) {
     tc::vel_net_tile_tc<ACT>(*ctl, is, which, outS, xs, ys, zs, ts, dphase, kphase, mode3);
+  }
+};
+
+// FP16-split tensor cores, operands in shared memory (mlp_h.cuh) — the product path
+struct HMlp {
+  static constexpr int kThreads = th::kThreads;
+  static constexpr int kLaunchThreads = th::kLaunchThreads;
+  static constexpr int kStages = 4;
+  static constexpr uint32_t kTmemCols = 256;   // D ping-pong
+  static constexpr size_t kBytes = 1024 + th::kTileBytes + (size_t)kStages * th::kStageBytes + sizeof(th::Ctl);
+  th::Ctl* ctl;
+  th::Issuer is;
+  uint32_t tile_u32, dphase, kphase;
+  __device__ void init(unsigned char* p, const NvfiLinear* n0, const NvfiLinear* n1, int) {
+    const uint32_t a = tc::smem_u32(p);
+    p += (1024u - (a & 1023u)) & 1023u;
+    tile_u32 = tc::smem_u32(p);
+    ctl = reinterpret_cast<th::Ctl*>(p + th::kTileBytes + (size_t)kStages * th::kStageBytes);
+    dphase = 0;
+    kphase = 0;
+    th::setup(*ctl, n0, n1, kTmemCols);
+    is.init(*ctl, tile_u32 + th::kTileBytes, kStages);
+  }
+  __device__ void finish() { th::teardown(*ctl, is, kTmemCols); }
+  template <int ACT>
+  __device__ void eval(int which, float* outS, const float* xs, const float* ys, const float* zs,
+                       const float* ts) {
+    th::vel_net_tile_h<ACT>(*ctl, is, which, outS, xs, ys, zs, ts, tile_u32, dphase, kphase);
   }
 };
 
@@ -240,6 +269,12 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
   sample_advect_body<TcMlp>(F, A, B, S, total, n_batches, mode, subs);
 }
 
+__global__ void __launch_bounds__(th::kLaunchThreads, 1)
+    k_sample_advect_h(const __grid_constant__ NvfiField F, const NvfiRenderArgs A,
+                      const NvfiRenderBuffers B, int S, long long total, int n_batches, int mode, int subs) {
+  sample_advect_body<HMlp>(F, A, B, S, total, n_batches, mode, subs);
+}
+
 // Chunk-global predicate of sample_ray (models/tensorf_base.py:294): one flag per chunk
 // of `ray_chunk` rays: any component of any origin inside [aabb_min, aabb_max].
 __global__ void k_chunk_inside(const NvfiField F, const float* __restrict__ rays_o, long long n,
@@ -321,6 +356,13 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
   integrate_pos_body<TcMlp>(F, x, t, base, n, out, counter, mode);
 }
 
+__global__ void __launch_bounds__(th::kLaunchThreads, 1)
+    k_integrate_pos_h(const __grid_constant__ NvfiField F, const float* __restrict__ x,
+                      const float* __restrict__ t, const float* __restrict__ base, long long n,
+                      float* __restrict__ out, int* counter, int mode) {
+  integrate_pos_body<HMlp>(F, x, t, base, n, out, counter, mode);
+}
+
 // VelBasis.forward (full != 0 -> (n,6) = [v, a]) or the gated velocity (n,3).
 template <class Mlp>
 __device__ __forceinline__ void velocity_body(const NvfiField& F, const float* __restrict__ xyzt,
@@ -394,6 +436,12 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
   velocity_body<TcMlp>(F, xyzt, n, full, out, counter, mode);
 }
 
+__global__ void __launch_bounds__(th::kLaunchThreads, 1)
+    k_velocity_h(const __grid_constant__ NvfiField F, const float* __restrict__ xyzt, long long n,
+                 int full, float* __restrict__ out, int* counter, int mode) {
+  velocity_body<HMlp>(F, xyzt, n, full, out, counter, mode);
+}
+
 }  // namespace nvfi
 
 using namespace nvfi;
@@ -415,6 +463,12 @@ extern "C" int nvfi_get_mlp_mode(void);
 static bool has_umma(const NvfiLinear* net) {
   for (int l = 0; l < NVFI_VEL_LAYERS; ++l)
     if (!net[l].umma || net[l].umma_rows != (l == NVFI_VEL_LAYERS - 1 ? 16 : 128)) return false;
+  return true;
+}
+
+static bool has_himg(const NvfiLinear* net) {
+  for (int l = 0; l < NVFI_VEL_LAYERS; ++l)
+    if (!net[l].himg) return false;
   return true;
 }
 
@@ -443,6 +497,19 @@ extern "C" int nvfi_launch_sample_advect(const NvfiField* F, const NvfiRenderArg
     return (int)cudaGetLastError();
   }
   const int mode = nvfi_get_mlp_mode();
+  if (mode == NVFI_MLP_F16X3) {
+    if (!has_himg(F->vel_net)) return NVFI_EINVAL;
+    const int subs = grab_subs(total, HMlp::kThreads, num_sms());
+    const int per_batch = subs * HMlp::kThreads;
+    const int n_batches = (int)((total + per_batch - 1) / per_batch);
+    const size_t smem = HMlp::kBytes + sizeof(SampleAdvectTail<HMlp::kThreads>);
+    static size_t cached = 0;
+    int rc = set_smem(k_sample_advect_h, smem, cached);
+    if (rc != NVFI_OK) return rc;
+    const int grid = min(n_batches, num_sms());
+    NVFI_LAUNCH(k_sample_advect_h, grid, HMlp::kLaunchThreads, smem, st, *F, *A, *B, S, total, n_batches, mode, subs);
+    return (int)cudaGetLastError();
+  }
   if (mode != NVFI_MLP_FP32_SIMT) {
     if (!has_umma(F->vel_net)) return NVFI_EINVAL;
     // raw samples per atomically grabbed batch: 8 x 512 for a frame, fewer for a training batch
@@ -477,6 +544,16 @@ extern "C" int nvfi_integrate_pos(const NvfiField* F, const float* x, const floa
   NVFI_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(int32_t), st));
   const long long n_tiles = (n + NVFI_TM - 1) / NVFI_TM;
   const int mode = nvfi_get_mlp_mode();
+  if (mode == NVFI_MLP_F16X3) {
+    if (!has_himg(F->vel_net)) return NVFI_EINVAL;
+    const size_t smem = HMlp::kBytes + sizeof(PointAdvectTail);
+    static size_t cached = 0;
+    int rc = set_smem(k_integrate_pos_h, smem, cached);
+    if (rc != NVFI_OK) return rc;
+    const int grid = (int)(n_tiles < (long long)num_sms() ? n_tiles : (long long)num_sms());
+    NVFI_LAUNCH(k_integrate_pos_h, grid, HMlp::kLaunchThreads, smem, st, *F, x, t, base, n, out, counters, mode);
+    return (int)cudaGetLastError();
+  }
   if (mode != NVFI_MLP_FP32_SIMT) {
     if (!has_umma(F->vel_net)) return NVFI_EINVAL;
     const size_t smem = TcMlp::kBytes + sizeof(PointAdvectTail);
@@ -504,6 +581,16 @@ extern "C" int nvfi_velocity(const NvfiField* F, const float* xyzt, int64_t n, i
   NVFI_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(int32_t), st));
   const long long n_tiles = (n + NVFI_TM - 1) / NVFI_TM;
   const int mode = nvfi_get_mlp_mode();
+  if (mode == NVFI_MLP_F16X3) {
+    if (!has_himg(F->vel_net) || (full && !has_himg(F->acc_net))) return NVFI_EINVAL;
+    const size_t smem = HMlp::kBytes + sizeof(PointAdvectTail);
+    static size_t cached = 0;
+    int rc = set_smem(k_velocity_h, smem, cached);
+    if (rc != NVFI_OK) return rc;
+    const int grid = (int)(n_tiles < (long long)num_sms() ? n_tiles : (long long)num_sms());
+    NVFI_LAUNCH(k_velocity_h, grid, HMlp::kLaunchThreads, smem, st, *F, xyzt, n, full, out, counters, mode);
+    return (int)cudaGetLastError();
+  }
   if (mode != NVFI_MLP_FP32_SIMT) {
     if (!has_umma(F->vel_net) || (full && !has_umma(F->acc_net))) return NVFI_EINVAL;
     const size_t smem = TcMlp::kBytes + sizeof(PointAdvectTail);

@@ -26,13 +26,13 @@ MAT_MODE_SPACE = ((0, 1), (0, 2), (1, 2))
 MAT_MODE_TIME = ((2, 3), (1, 3), (0, 3))
 
 
-MLP_MODES = {"simt": L.MLP_FP32_SIMT, "tf32x3": L.MLP_TF32X3, "tf32": L.MLP_TF32}
+MLP_MODES = {"simt": L.MLP_FP32_SIMT, "tf32x3": L.MLP_TF32X3, "tf32": L.MLP_TF32, "f16x3": L.MLP_F16X3}
 
 
 def set_mlp_mode(mode: str) -> str:
-    """Arithmetic of the velocity-MLP GEMMs: 'tf32x3' (tcgen05 tensor cores, FP32-grade 3-term
-    split; default), 'tf32' (single pass, fastest) or 'simt' (FP32 FMA verification path).
-    Returns the previous mode."""
+    """Arithmetic of the velocity-MLP GEMMs: 'f16x3' (tcgen05 FP16 tensor cores, 2-way operand split,
+    FP32-grade; default), 'tf32x3' (round-1 path: 3-term TF32 split, activations in tensor memory),
+    'tf32' (single TF32 pass) or 'simt' (FP32 FMA verification path).  Returns the previous mode."""
     prev = L.load().nvfi_set_mlp_mode(MLP_MODES[mode])
     if prev < 0:
         raise RuntimeError("nvfi_b200: bad mlp mode")
@@ -94,6 +94,16 @@ class PackedLinear:
         self.ummaT_rows = (128 if in_dim == 128 else _round_up(in_dim, 32)) if (umma and diff and hidden) else 0
         self.ummaT = (torch.zeros((128 // 32) * 2 * self.ummaT_rows * 32, device=device, dtype=torch.float32)
                       if self.ummaT_rows else None)
+        # FP16-split images (mlp_h.cuh): rows x K padded to 64, hi slab + lo slab per 64-wide K block
+        self.h_rows = self.umma_rows
+        self.h_kpad = _round_up(in_dim, 64)
+        self.himg = (torch.zeros((self.h_kpad // 64) * self.h_rows * 256, device=device, dtype=torch.uint8)
+                     if umma else None)
+        # W^T image: rows = input features (128; 32 for the 28-wide first layer), K = outputs padded to 64
+        self.hT_rows = (_round_up(in_dim, 32) if umma and diff else 0)
+        self.hT_kpad = _round_up(out_dim, 64)
+        self.himgT = (torch.zeros((self.hT_kpad // 64) * self.hT_rows * 256, device=device, dtype=torch.uint8)
+                      if self.hT_rows else None)
         self.track = _Tracked()
 
     def sync(self, w: torch.Tensor, b: Optional[torch.Tensor]):
@@ -114,6 +124,12 @@ class PackedLinear:
             wT = wd.t().contiguous()      # (in, out): "out_dim" = input features, K = 128 outputs
             L.check(lib.nvfi_pack_linear_umma(wT.data_ptr(), self.ummaT.data_ptr(), self.in_dim, self.out_dim,
                                               self.ummaT_rows, 128, _stream()), "pack_linear_umma(T)")
+        if self.himg is not None:
+            L.check(lib.nvfi_pack_linear_h(wd.data_ptr(), self.himg.data_ptr(), self.out_dim, self.in_dim,
+                                           self.h_rows, self.h_kpad, 0, _stream()), "pack_linear_h")
+        if self.himgT is not None:
+            L.check(lib.nvfi_pack_linear_h(wd.data_ptr(), self.himgT.data_ptr(), self.out_dim, self.in_dim,
+                                           self.hT_rows, self.hT_kpad, 1, _stream()), "pack_linear_h(T)")
 
     def fill(self, s: L.NvfiLinear):
         s.wt = self.wt.data_ptr()
@@ -123,6 +139,8 @@ class PackedLinear:
         s.umma_rows = self.umma_rows
         s.ummaT = _ptr(self.ummaT)
         s.ummaT_rows = self.ummaT_rows
+        s.himg = _ptr(self.himg)
+        s.himgT = _ptr(self.himgT)
         s.in_dim, s.out_dim, s.k_pad, s.n_pad = self.in_dim, self.out_dim, self.k_pad, self.n_pad
 
     def unpack_grad(self, g_wt: torch.Tensor, g_b: Optional[torch.Tensor], want_bias: bool):

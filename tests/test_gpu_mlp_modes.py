@@ -1,14 +1,15 @@
 """The velocity-MLP GEMMs run either on the FP32 SIMT verification path or on the tcgen05
-tensor cores (3-term TF32 split = FP32-grade, the default; single TF32 pass = fast mode).
-Every mode is held against the same golden vectors; the tolerance is the north-star 1e-4
-for 'simt' and 'tf32x3' and a stated, looser bound for the single-pass fast mode."""
+tensor cores: FP16 2-way operand split (hi + lo = 22 mantissa bits, 3 MMAs per GEMM; the default),
+the round-1 3-term TF32 split, or a single TF32 pass.  Every mode is held against the same golden
+vectors; the tolerance is the north-star 1e-4 for 'simt', 'f16x3' and 'tf32x3' and a stated, looser
+bound for the single-pass mode."""
 import pytest
 import torch
 
 from tests.helpers import GOLDEN_SCENES, Golden, build_model, rel_err
 
 pytestmark = pytest.mark.gpu
-TOL = {"simt": 1e-4, "tf32x3": 1e-4, "tf32": 2e-2}
+TOL = {"simt": 1e-4, "f16x3": 1e-4, "tf32x3": 1e-4, "tf32": 2e-2}
 
 
 @pytest.fixture(scope="module", params=GOLDEN_SCENES)
@@ -21,7 +22,7 @@ def model(g):
     return build_model(g)
 
 
-@pytest.fixture(params=["simt", "tf32x3", "tf32"])
+@pytest.fixture(params=["simt", "f16x3", "tf32x3", "tf32"])
 def mode(request):
     from nvfi_b200 import engine
     prev = engine.set_mlp_mode(request.param)
@@ -33,7 +34,7 @@ def test_default_mode_is_tensor_core():
     from nvfi_b200 import _lib
     import os
     if "NVFI_MLP_MODE" not in os.environ:
-        assert _lib.load().nvfi_get_mlp_mode() == _lib.MLP_TF32X3
+        assert _lib.load().nvfi_get_mlp_mode() == _lib.MLP_F16X3
 
 
 def test_velocity_and_advection(g, model, mode):
@@ -90,9 +91,12 @@ def test_modes_agree_on_large_batch(model, g):
         ref = f.vel_net(xt)
         engine.set_mlp_mode("tf32x3")
         got = f.vel_net(xt)
+        engine.set_mlp_mode("f16x3")
+        got_h = f.vel_net(xt)
     finally:
         engine.set_mlp_mode(prev)
     assert rel_err(got.cpu(), ref.cpu()) < 2e-5
+    assert rel_err(got_h.cpu(), ref.cpu()) < 2e-5
 
 
 @pytest.mark.parametrize("i", range(2))
