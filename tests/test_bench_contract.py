@@ -55,5 +55,5 @@ def test_gpu_arm_line():
     assert r["bound"] in ("hbm", "tensor") and 0 < r["frac"] and r["peak"] > 0
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert set(j["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
-    assert "k_march" in j["kernels"] and "k_sample_advect_tc" in j["kernels"]
+    assert "k_march" in j["kernels"] and "k_sample_advect_h" in j["kernels"]
     assert j["invalid_for_bench"]          # a 40-row band is a profiling aid, not the bench workload

@@ -19,6 +19,7 @@ rows = list(csv.reader(io.StringIO(out)))
 hdr, units = rows[0], rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 unit_of = {"k_advect_bwd_tc": "advected_samples_bwd", "k_sample_advect_tc": "advected_samples",
+           "k_advect_bwd_h": "advected_samples_bwd", "k_sample_advect_h": "advected_samples",
            "k_march": "valid_samples", "k_density_bwd": "valid_samples"}
 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 res = {"source": f"{rep} (ncu --set full --clock-control none, bench.py --rows 50)", "counts": counts, "kernels": {}}
