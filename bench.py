@@ -68,50 +68,106 @@ def workload_config(world):
 # CPU leg (oracle port of the reference algorithm)
 # ------------------------------------------------------------------------------------------
 class CpuLeg:
-    """Reference algorithm (oracle port) on the host: train render fwd + MSE + backward on
-    2048-ray chunks of the same frame, all host threads."""
+    """The reference's CPU path on the host: train render fwd + MSE + backward on 2 048-ray chunks
+    of the same frame (the reference's own chunk size), all host threads.
+
+    kind "reference": the UNMODIFIED reference (models.Renderer.render + autograd) imported from
+    baseline/_ref (tools/install_reference.py; git-ignored, shipped to the GPU box);
+    kind "port": the oracle restatement (oracle/nvfi_oracle.py), used when baseline/_ref is absent.
+    Chunks are taken at a stride across the WHOLE frame (the frame has 313 chunks; stride 37 is
+    coprime), so the sample sees empty borders and the cube in the frame's proportions; the valid-
+    sample fraction of the sample is reported next to the frame's."""
+
+    STRIDE = 37
 
     def __init__(self):
         from nvfi_b200 import configs, synth
         from nvfi_b200.scenes import frame_rays
-        from oracle.scene_io import scene_from_state
+        from oracle import reference_loader
 
         self.cores = os.cpu_count() or 1
         torch.set_num_threads(self.cores)
         cfg = configs.get_config("bat", step_ratio=STEP_RATIO)
         K = int(cfg.nvfi.num_keyframes)
         sd = synth.synth_state(cfg, list(GRID), K, seed=233)
-        self.sc = scene_from_state(cfg, list(GRID), K, sd, requires_grad=True)
-        self.o, self.d = frame_rays(H, W)
+        ref_path = reference_loader.find_reference(allow_checkout=False)
+        if ref_path is not None:
+            self.kind = "reference"
+            self.ref_models, _, self.nv = reference_loader.build_reference(ref_path, cfg, GRID, K, sd)
+            self.nv.requires_grad_(True)
+            self.renderer = self.ref_models.Renderer(self.nv, 0, 0, RAY_CHUNK)
+            self.field = self.nv.nvfi
+        else:
+            from oracle.scene_io import scene_from_state
+            self.kind = "port"
+            self.sc = scene_from_state(cfg, list(GRID), K, sd, requires_grad=True)
+        self.o, self.d = frame_rays(H, W, theta=30.0)
+        self.n_chunks = (self.o.shape[0] + RAY_CHUNK - 1) // RAY_CHUNK
         self.gen = torch.Generator().manual_seed(7)
         self.next_chunk = 0
+        self.valid = 0
+        self.samples = 0
+
+    def _valid_fraction(self, oo, dd):
+        """Share of in-box samples of a chunk (the reference's own sampler, eval spacing)."""
+        from oracle import nvfi_oracle as O
+        with torch.no_grad():
+            if self.kind == "reference":
+                was = self.field.training
+                self.field.eval()
+                valid = self.field.sample_ray(oo, dd, N_samples=-1)[2]
+                self.field.train(was)
+            else:
+                valid = O.sample_ray(self.sc, oo, dd, None)[2]
+        return int(valid.sum()), int(valid.numel())
 
     def run(self, budget_s: float, chunks_cap: int):
-        """Returns (seconds, rays) for up to `chunks_cap` chunks or `budget_s` seconds."""
-        from oracle import nvfi_oracle as O
-        start = (H // 2) * W    # chunks from the middle of the frame (rays that hit the cube)
+        """Returns (seconds, rays, chunks) for up to `chunks_cap` chunks or `budget_s` seconds."""
         done, t_total, k = 0, 0.0, 0
         while k < chunks_cap and (k < 1 or t_total < budget_s):
-            c = self.next_chunk % 64
-            sl = slice(start + c * RAY_CHUNK, start + (c + 1) * RAY_CHUNK)
+            c = (self.next_chunk * self.STRIDE + 5) % self.n_chunks
+            sl = slice(c * RAY_CHUNK, min((c + 1) * RAY_CHUNK, self.o.shape[0]))
             oo, dd = self.o[sl], self.d[sl]
-            jit = torch.rand(oo.shape[0], 1, generator=self.gen)
             target = torch.rand(oo.shape[0], 3, generator=self.gen)
-            for p in self.sc.parameters():
-                p.grad = None
-            t0 = time.perf_counter()
-            out = O.render_chunk(self.sc, T_RENDER, oo, dd, white_bg=True, training=True, jitter=jit)
-            loss = torch.nn.functional.mse_loss(out[0], target)
-            loss.backward()
-            t_total += time.perf_counter() - t0
+            if self.kind == "reference":
+                for p in self.nv.parameters():
+                    p.grad = None
+                t0 = time.perf_counter()
+                out = self.renderer.render(T_RENDER, self.ref_models.Ray(oo, dd, 0, 0), white_background=True,
+                                           mode="train")
+                loss = torch.nn.functional.mse_loss(out[0], target)
+                loss.backward()
+                t_total += time.perf_counter() - t0
+            else:
+                from oracle import nvfi_oracle as O
+                jit = torch.rand(oo.shape[0], 1, generator=self.gen)
+                for p in self.sc.parameters():
+                    p.grad = None
+                t0 = time.perf_counter()
+                out = O.render_chunk(self.sc, T_RENDER, oo, dd, white_bg=True, training=True, jitter=jit)
+                loss = torch.nn.functional.mse_loss(out[0], target)
+                loss.backward()
+                t_total += time.perf_counter() - t0
+            try:
+                v, tot = self._valid_fraction(oo, dd)
+                self.valid += v
+                self.samples += tot
+            except Exception:
+                pass
             done += oo.shape[0]
             k += 1
             self.next_chunk += 1
         return t_total, done, k
 
-
-def cpu_sample_desc(k):
-    return f"{k} chunks x {RAY_CHUNK} rays from the frame centre, fwd+MSE+bwd, t={T_RENDER}"
+    def describe(self, k, frame_valid_fraction=None):
+        s = (f"{k} chunks x {RAY_CHUNK} rays at stride {self.STRIDE} across the {self.n_chunks} chunks of the frame, "
+             f"fwd+MSE+bwd, t={T_RENDER}, "
+             + ("unmodified reference (baseline/_ref) on CPU" if self.kind == "reference" else "oracle port on CPU"))
+        if self.samples:
+            s += f"; valid-sample fraction of the sample {self.valid / self.samples:.3f}"
+            if frame_valid_fraction is not None:
+                s += f" (whole frame {frame_valid_fraction:.3f})"
+        return s
 
 
 def run_reference(args):
@@ -122,18 +178,19 @@ def run_reference(args):
     leg = CpuLeg()
     for _ in range(warm):
         leg.run(0.0, 1)
-    t_sum, r_sum = 0.0, 0
+    t_sum, r_sum, k_sum = 0.0, 0, 0
     for _ in range(steps):      # each step = a bounded sample of the frame: 2 chunks
-        tt, rr, _ = leg.run(1e9, 2)
+        tt, rr, kk = leg.run(1e9, 2)
         t_sum += tt
         r_sum += rr
+        k_sum += kk
     value = r_sum / t_sum
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": 1e3 * t_sum / steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(world),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": leg.cores, "kind": "port",
-                             "sample": cpu_sample_desc(2) + " per step"},
+            "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": leg.cores, "kind": leg.kind,
+                             "sample": leg.describe(k_sum)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -419,9 +476,10 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu:
             leg = CpuLeg()
             leg.run(0.0, 1)     # warm-up chunk (thread pool, allocator)
-            tt, rr, k = leg.run(args.cpu_budget, 8)
-            line["cpu_baseline"] = {"value": rr / tt, "unit": UNIT, "cores": leg.cores, "kind": "port",
-                                    "sample": cpu_sample_desc(k)}
+            leg.valid = leg.samples = 0
+            tt, rr, k = leg.run(args.cpu_budget, 10)
+            line["cpu_baseline"] = {"value": rr / tt, "unit": UNIT, "cores": leg.cores, "kind": leg.kind,
+                                    "sample": leg.describe(k, n_valid / float(n * 192))}
         if args.rows != H:
             line["invalid_for_bench"] = f"profiling run on {args.rows} of {H} rows"
         print(json.dumps(line), flush=True)

@@ -170,6 +170,10 @@ typedef struct NvfiRenderBuffers {
                             nvfi_render_backward, the int64 at [8] / [10] holds the number of
                             samples back-propagated through the appearance / velocity nets */
   int64_t* stats;        /* >= 4: [valid samples, advected samples, app samples, 0], or NULL */
+  float* x_mid;          /* optional (n_rays, S, 3): RK2 midpoint of the last advection step of every valid
+                            sample, saved by a training forward so that the backward pass need not re-evaluate
+                            the first velocity evaluation to find it (used when the call has ONE step); NULL =
+                            recompute */
 } NvfiRenderBuffers;
 
 /* Upstream gradients and gradient accumulators for the backward pass.  Plane

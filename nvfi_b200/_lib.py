@@ -68,6 +68,7 @@ class NvfiRenderBuffers(C.Structure):
         ("weights", C.c_void_p), ("mask_map", C.c_void_p), ("x_adv", C.c_void_p),
         ("valid", C.c_void_p), ("rgb", C.c_void_p), ("sigma", C.c_void_p),
         ("chunk_inside", C.c_void_p), ("counters", C.c_void_p), ("stats", C.c_void_p),
+        ("x_mid", C.c_void_p),
     ]
 
 

@@ -24,6 +24,25 @@
 // component is in [8, 16) (12 binades of headroom for growth through the layers, 2^-29 of the tile
 // maximum as absolute resolution); every result is unscaled when it leaves the tensor cores.
 #include "backward_common.cuh"
+
+#ifdef NVFI_TIMELINE
+// (tag, clock64) pairs of CTA 0: who = 0 -> worker thread 0 (first half of the buffer), who = 1 -> lane 0 of
+// the issuer warp (second half)
+__device__ long long* g_tlh_buf = nullptr;
+__device__ int g_tlh_cap = 0;
+__device__ int g_tlh_n[2] = {0, 0};
+__device__ __forceinline__ void tlh_mark(int tag, int who) {
+  if (blockIdx.x == 0 && threadIdx.x == (who ? 512 : 0) && g_tlh_buf != nullptr) {
+    const int i = g_tlh_n[who], half = g_tlh_cap / 2;
+    if (i + 2 <= half) {
+      g_tlh_buf[who * half + i] = tag;
+      g_tlh_buf[who * half + i + 1] = clock64();
+      g_tlh_n[who] = i + 2;
+    }
+  }
+}
+#define NVFI_TLH(tag, who) tlh_mark((tag), (who))
+#endif
 #include "mlp_h.cuh"
 
 namespace nvfi {
@@ -33,21 +52,23 @@ constexpr int NT = th::kThreads;            // 512 worker threads (+ the issuer 
 constexpr uint32_t kStages = 2;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColD0 = 0;              // input-gradient accumulator (forward evaluations: 0 / 128)
-constexpr uint32_t kColD1 = 256;            // weight-gradient accumulator
-constexpr uint32_t kColDb = 384;            // column sums of G_l (16 columns)
-constexpr uint32_t kColDh = 400;            // head weight gradient (16 columns)
+constexpr uint32_t kColD1 = 256;            // weight-gradient accumulators: layer l -> 256 + 128 (l & 1)
+constexpr uint32_t kColDh = 384;            // head weight gradient (16 columns; read before layer 3 writes there)
 
 // per-CTA global scratch (byte offsets)
 constexpr size_t kWsStashA = 0;
 constexpr size_t kWsStashS = th::kStashABytes;
 constexpr size_t kWsXsteps = kWsStashS + th::kStashSFloats * sizeof(float);
-constexpr size_t kWsBytes = kWsXsteps + (size_t)MAX_RK2_STEPS * 3 * NVFI_TM * sizeof(float);
+constexpr size_t kWsPart = kWsXsteps + (size_t)MAX_RK2_STEPS * 3 * NVFI_TM * sizeof(float);
+// per-CTA partial weight gradients in the packed (k_pad, n_pad) layout: layer 0 (32 x 128), layers 1..4
+constexpr int kPartF = 32 * NVFI_TM + 4 * NVFI_TM * NVFI_TM;
+__host__ __device__ constexpr int part_off(int l) { return l == 0 ? 0 : 32 * NVFI_TM + (l - 1) * NVFI_TM * NVFI_TM; }
+constexpr size_t kWsBytes = kWsPart + (size_t)kPartF * sizeof(float);
 static_assert(kWsBytes <= (size_t)WS_CTA_F * sizeof(float), "per-CTA workspace of k_advect_bwd_h exceeds WS_CTA_F");
 
 struct BwdTile {
   alignas(128) unsigned char gw_hi[4096];   // upstream gradient of the head, [128 samples][16] FP16 (no swizzle)
   alignas(128) unsigned char gw_lo[4096];
-  alignas(128) unsigned char ones[512];     // [16][16] FP16 1.0
   float x0[3][NVFI_TM];
   float xm[3][NVFI_TM];
   float gbar[3][NVFI_TM];
@@ -65,7 +86,13 @@ struct BwdTile {
   th::Issuer iss;           // weight-ring state of the issuer warp between calls
 };
 
-__device__ __forceinline__ float ldcg_now(const float* p) {
+// ld.global.cg as a volatile asm: consecutive calls are issued back to back
+__device__ __forceinline__ float4 ldcg4_now(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldcg_f(const float* p) {
   float v;
   asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
@@ -73,8 +100,25 @@ __device__ __forceinline__ float ldcg_now(const float* p) {
 __device__ __forceinline__ void red_add(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
-__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+// Sum over the 32 rows (lanes) of a warp of 8 per-lane values: lane j returns the sum of v[j & 7].
+// Butterfly: 7 exchanges that halve the value count, then 2 plain ones.
+__device__ __forceinline__ float colsum8(const float v[8], int lane) {
+  float w4[4], w2[2];
+  const bool u4 = lane & 4, u2 = lane & 2, u1 = lane & 1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = u4 ? v[i] : v[i + 4], keep = u4 ? v[i + 4] : v[i];
+    w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = u2 ? w4[i] : w4[i + 2], keep = u2 ? w4[i + 2] : w4[i];
+    w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  float w = (u1 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, u1 ? w2[0] : w2[1], 1);
+  w += __shfl_xor_sync(0xffffffffu, w, 8);
+  w += __shfl_xor_sync(0xffffffffu, w, 16);
+  return w;
 }
 
 // ---- backward through one weight-net evaluation -------------------------------------------
@@ -84,11 +128,11 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
 // and head gradients to the register accumulators.  Whole CTA (13 block barriers).
 __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint32_t tA, uint32_t tG,
                            const NvfiRenderGrads& D, const unsigned char* __restrict__ stash_a,
-                           const float* __restrict__ stash_s, const float* xs, const float* ys, const float* zs,
-                           uint32_t& dphase, uint32_t& wphase, uint32_t& aphase, float (&acc_head)[6],
-                           float (&acc_bias)[6]) {
+                           const float* __restrict__ stash_s, float* __restrict__ part, const float* xs,
+                           const float* ys, const float* zs, uint32_t& dphase, uint32_t& wphase, uint32_t& aphase,
+                           float (&acc_head)[6], float (&acc_bias)[6]) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t gw_hi = tc::smem_u32(T.gw_hi), gw_lo = tc::smem_u32(T.gw_lo), ones = tc::smem_u32(T.ones);
+  const uint32_t gw_hi = tc::smem_u32(T.gw_hi), gw_lo = tc::smem_u32(T.gw_lo);
 
   // ---- scale of the tile: largest |dL/dw| -> [8, 16)
   if (tid < NVFI_TM) {
@@ -112,9 +156,11 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
 
   if (warp == th::kIssuerWarp) {   // ==================================================== issuer warp
     th::Issuer is = is_shared;
+    NVFI_TLH(1100, 1);
     th::ring_top_up(c, is, false);
     __syncthreads();   // (A) upstream-gradient tile written
     tc::tc_fence_after();
+    NVFI_TLH(1101, 1);
     const uint32_t tb = is.tb;
     const uint32_t id128 = th::idesc_f16(128), id32 = th::idesc_f16(32);
     const uint32_t hs = th::kDescHiSw128;
@@ -149,7 +195,10 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
       tc::tc_commit(&c.wbar);
     }
     __syncwarp();
+    NVFI_TLH(1102, 1);
     tc::mbar_wait(&c.wbar, wphase & 1);   // A_4 consumed: tile tA is free
+    ++wphase;
+    NVFI_TLH(1103, 1);
     if (tc::elect_one()) {
       tc::mbar_expect_tx(&c.abar, th::kTileBytes);
       tc::bulk_g2s_u32(tA, stash_a + 32768 + (size_t)3 * th::kTileBytes, th::kTileBytes, &c.abar);   // A_3
@@ -158,6 +207,7 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
     th::ring_top_up(c, is, false);
     __syncthreads();   // (B) G_4 in tile tG
     tc::tc_fence_after();
+    NVFI_TLH(1104, 1);
     // dX of layer l: D0[m][k] = sum_n G_l[m][n] W_l[n][k]
     auto issue_dx = [&](int l) {
       const uint32_t nx = (l == 0) ? 32u : 128u;
@@ -180,57 +230,55 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
         }
         __syncwarp();
         th::ring_advance(is);
-        th::ring_top_up(c, is, false);
       }
     };
     issue_dx(4);
 #pragma unroll 1
     for (int l = 4; l >= 0; --l) {
+      NVFI_TLH(1105, 1);
       tc::mbar_wait(&c.abar, aphase & 1);   // A_{l-1} (l = 0: the encoding) is in tile tA
       ++aphase;
       tc::tc_fence_after();
+      NVFI_TLH(1110 + l, 1);
       if (tc::elect_one()) {
-        // dW: D1[n][k] = sum_m G_l[m][n] A_{l-1}[m][k]; db: Db[n][.] = sum_m G_l[m][n]
-        const uint32_t idw = th::idesc_f16(l == 0 ? 32 : 128, 1, 1), idb = th::idesc_f16(16, 1, 0);
-        const uint32_t o_h = th::desc_lo(ones, 128);
+        // dW: D1[n][k] = sum_m G_l[m][n] A_{l-1}[m][k]
+        const uint32_t idw = th::idesc_f16(l == 0 ? 32 : 128, 1, 1);
+        const uint32_t d1 = tb + kColD1 + 128u * (uint32_t)(l & 1);
 #pragma unroll 2
         for (uint32_t ks = 0; ks < 8; ++ks) {
           const uint32_t g_h = th::desc_lo(tG + ks * 2048u, 16384), g_l = th::desc_lo(tG + th::kLoOff + ks * 2048u, 16384);
           const uint32_t a_h = th::desc_lo(tA + ks * 2048u, 16384), a_l = th::desc_lo(tA + th::kLoOff + ks * 2048u, 16384);
-          th::mma_f16_ss(tb + kColD1, g_h, hs, a_h, hs, idw, ks ? 1u : 0u);
-          th::mma_f16_ss(tb + kColD1, g_l, hs, a_h, hs, idw, 1u);
-          th::mma_f16_ss(tb + kColD1, g_h, hs, a_l, hs, idw, 1u);
-          th::mma_f16_ss(tb + kColDb, g_h, hs, o_h, th::kDescHiSmallK, idb, ks ? 1u : 0u);
-          th::mma_f16_ss(tb + kColDb, g_l, hs, o_h, th::kDescHiSmallK, idb, 1u);
+          th::mma_f16_ss(d1, g_h, hs, a_h, hs, idw, ks ? 1u : 0u);
+          th::mma_f16_ss(d1, g_l, hs, a_h, hs, idw, 1u);
+          th::mma_f16_ss(d1, g_h, hs, a_l, hs, idw, 1u);
         }
         tc::tc_commit(&c.wbar);
       }
       __syncwarp();
-      __syncthreads();   // (C1) G_{l-1} in tile tG
-      tc::tc_fence_after();
-      if (l > 0) issue_dx(l - 1);
-      __syncthreads();   // (C2) D1 staged (transposed) in tile tA
-      if (tc::elect_one()) {
-        th::bulk_reduce_add_f32(D.g_vel_w[l], tA, l == 0 ? 16384u : 65536u);
-        th::bulk_commit();
-        if (l > 0) {
-          th::bulk_wait_read0();   // the staging rows have been read: the tile may be overwritten
-          if (l >= 2) {
-            tc::mbar_expect_tx(&c.abar, th::kTileBytes);
-            tc::bulk_g2s_u32(tA, stash_a + 32768 + (size_t)(l - 2) * th::kTileBytes, th::kTileBytes, &c.abar);
-          } else {   // the encoding: columns 0..31 of slab 0, hi and lo
-            tc::mbar_expect_tx(&c.abar, 2u * th::kSlab);
-            tc::bulk_g2s_u32(tA, stash_a, th::kSlab, &c.abar);
-            tc::bulk_g2s_u32(tA + th::kLoOff, stash_a + th::kSlab, th::kSlab, &c.abar);
-          }
-        } else {
-          th::bulk_wait_read0();
+      NVFI_TLH(1120 + l, 1);
+      th::ring_top_up(c, is, false);        // dX(l) is done by now: its stages take the next layer's W^T blocks
+      tc::mbar_wait(&c.wbar, wphase & 1);   // dW(l) done: tile tA is free for A_{l-2}
+      ++wphase;
+      th::ring_top_up(c, is, false);
+      if (l > 0 && tc::elect_one()) {
+        if (l >= 2) {
+          tc::mbar_expect_tx(&c.abar, th::kTileBytes);
+          tc::bulk_g2s_u32(tA, stash_a + 32768 + (size_t)(l - 2) * th::kTileBytes, th::kTileBytes, &c.abar);
+        } else {   // the encoding: columns 0..31 of slab 0, hi and lo
+          tc::mbar_expect_tx(&c.abar, 2u * th::kSlab);
+          tc::bulk_g2s_u32(tA, stash_a, th::kSlab, &c.abar);
+          tc::bulk_g2s_u32(tA + th::kLoOff, stash_a + th::kSlab, th::kSlab, &c.abar);
         }
       }
       __syncwarp();
+      NVFI_TLH(1130 + l, 1);
+      __syncthreads();   // (C1) G_{l-1} in tile tG
+      tc::tc_fence_after();
+      NVFI_TLH(1140 + l, 1);
+      if (l > 0) issue_dx(l - 1);
+      NVFI_TLH(1150 + l, 1);
     }
     dphase += 6;
-    wphase += 6;
     is_shared = is;
     return;
   }
@@ -260,24 +308,31 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
   if (warp < 6)     // db5[n] = sum_m gout[n][m]: warp n, each lane 4 samples (reduced at kernel end)
     acc_bias[5] += T.gout[warp][lane] + T.gout[warp][lane + 32] + T.gout[warp][lane + 64] + T.gout[warp][lane + 96];
   tc::tc_fence_before();
+  NVFI_TLH(100, 0);
   __syncthreads();   // (A)
+  NVFI_TLH(101, 0);
   if (tid == 0) T.gmax = 0u;
 
+  // S_l[unit][sample] of this thread's 32 columns: coalesced 16-byte loads, issued one phase ahead
+  float4 sv[4][2];
+  auto load_s = [&](int l) {
+    const float4* sp = reinterpret_cast<const float4*>(stash_s) + ((size_t)l * 32 + h * 2) * NVFI_TM + m;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      sv[g][0] = ldcg4_now(sp + (size_t)(g * 8) * NVFI_TM);
+      sv[g][1] = ldcg4_now(sp + (size_t)(g * 8 + 1) * NVFI_TM);
+    }
+  };
+  load_s(4);
 #pragma unroll 1
   for (int L = 5; L >= 0; --L) {
-    // ---- S_{L-1}[unit][sample] of this thread's 32 columns: coalesced loads, issued before the wait
-    float sv[4][8];
-    if (L > 0) {
-      const float* sp = stash_s + ((size_t)(L - 1) * NVFI_TM + h * 8) * NVFI_TM + m;
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sv[g][i] = ldcg_now(sp + (size_t)(g * 32 + i) * NVFI_TM);
-    }
+    NVFI_TLH(110 + L, 0);
     tc::mbar_wait(&c.dbar, dphase & 1);   // D0 = dX(L)
     ++dphase;
     tc::tc_fence_after();
+    NVFI_TLH(120 + L, 0);
     uint4 ghi[4], glo[4];
+    float bsum = 0.f;
     if (L > 0) {
       // G_{L-1} = D0 (.) S_{L-1}, FP16 split, held in registers until tile tG is free
       const uint32_t dcol = tb + lane_base + kColD0 + (uint32_t)(h * 8);
@@ -287,11 +342,17 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
       tc::tmem_ld_wait();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
+        const float s8[8] = {sv[g][0].x, sv[g][0].y, sv[g][0].z, sv[g][0].w, sv[g][1].x, sv[g][1].y, sv[g][1].z, sv[g][1].w};
         float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[g][i]) * sv[g][i];
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[g][i]) * s8[i];
         th::split8(v, ghi[g], glo[g]);
+        // bias gradient of layer L - 1: column sums of G_{L-1} over the warp's 32 samples; lane j keeps
+        // column 32 (j >> 3) + 8 h + (j & 7)
+        const float cs = colsum8(v, lane);
+        if ((lane >> 3) == g) bsum = cs;
       }
+      acc_bias[L - 1] = fmaf(bsum, inv_scale, acc_bias[L - 1]);
     } else if (h == 0) {
       // dL/d(encoding) -> dL/d(x, y, z)  (encoder tangents)
       float ge[32];
@@ -308,9 +369,11 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
                                     4.f * (ge[20 + i] * c4 - ge[24 + i] * s4));
       }
     }
-    tc::mbar_wait(&c.wbar, wphase & 1);   // dW(L) and db(L) done: tiles tG and tA are free
+    NVFI_TLH(130 + L, 0);
+    tc::mbar_wait(&c.wbar, wphase & 1);   // dW(L) done: tiles tG and tA are free
     ++wphase;
     tc::tc_fence_after();
+    NVFI_TLH(140 + L, 0);
     if (L > 0) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -322,6 +385,8 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
     }
     tc::tc_fence_before();
     __syncthreads();   // (B) for the head, (C1) for the hidden layers
+    NVFI_TLH(150 + L, 0);
+    if (L >= 2) load_s(L - 2);   // for the next layer's epilogue, under this layer's flush
     if (L == 5) {
       if (h == 0) {   // dW5^T[k][n]: unit k = m
         uint32_t r[8];
@@ -332,28 +397,24 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
       }
       continue;
     }
-    // ---- D1[n][k] -> staging rows stage[k][n] in tile tA (this thread: n = m, k = 32 h + i); the issuer
-    //      adds the block to the packed gradient with one bulk reduction
+    // ---- D1[n][k] (this thread: n = m, k = 32 h + i) is added to the CTA's private partial gradient
+    //      part[k][n]: plain read-modify-write of addresses only this thread ever touches, 128 contiguous
+    //      bytes per warp instruction; it overlaps the next layer's MMAs (D1 ping-pongs in tensor memory)
     if (L > 0 || h == 0) {
+      float* pp = part + part_off(L) + (size_t)(h * 32) * NVFI_TM + m;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        float dv[16];
-        tc::tmem_ld16(tb + lane_base + kColD1 + (uint32_t)(h * 32 + half * 16), dv);
-        const uint32_t sa = tA + (uint32_t)(((h * 32 + half * 16) * NVFI_TM + m) * 4);
+        float old[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa + (uint32_t)(i * NVFI_TM * 4)), "f"(dv[i] * inv_scale) : "memory");
+        for (int i = 0; i < 16; ++i) old[i] = ldcg_f(pp + (size_t)(half * 16 + i) * NVFI_TM);
+        float dv[16];
+        tc::tmem_ld16(tb + lane_base + kColD1 + 128u * (uint32_t)(L & 1) + (uint32_t)(h * 32 + half * 16), dv);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) __stcg(pp + (size_t)(half * 16 + i) * NVFI_TM, fmaf(dv[i], inv_scale, old[i]));
       }
     }
-    if (h == 0) {
-      uint32_t r;
-      tmem_ld1(tb + lane_base + kColDb, r);
-      tc::tmem_ld_wait();
-      acc_bias[L] = fmaf(__uint_as_float(r), inv_scale, acc_bias[L]);
-    }
-    th::fence_async_smem();
-    tc::tc_fence_before();
-    __syncthreads();   // (C2)
+    tc::tc_fence_before();   // the D1 reads are ordered before the next barrier (the issuer reuses D1 two layers on)
+    NVFI_TLH(160 + L, 0);
   }
 }
 
@@ -390,6 +451,9 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
   unsigned char* stash_a = ws + kWsStashA;
   float* stash_s = reinterpret_cast<float*>(ws + kWsStashS);
   float* xsteps = reinterpret_cast<float*>(ws + kWsXsteps);
+  float* part = reinterpret_cast<float*>(ws + kWsPart);
+  for (int i = threadIdx.x; i < kPartF / 4; i += blockDim.x)   // the CTA's partial weight gradients start at zero
+    reinterpret_cast<float4*>(part)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // uniform RK2 schedule of this render call (models/tensorf_keyframe.py:577-609)
   float sched_dt[MAX_RK2_STEPS], sched_t[MAX_RK2_STEPS];
@@ -407,6 +471,8 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
     }
   }
 
+  // with the midpoints saved by the forward pass (single-step calls) the evaluation that only finds them is skipped
+  const bool use_mid = (B.x_mid != nullptr) && n_steps == 1;
   th::setup(ctl, F.vel_net, nullptr, kTmemCols);
   if (tid == 0) {   // weight segments in the order one tile consumes them
     int n = 0;
@@ -414,8 +480,8 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
       ctl.prog[n++] = th::SEG_FWD0;
       ctl.prog[n++] = th::SEG_FWD0;
     }
-    for (int k = 0; k < n_steps; ++k) {   // F1', F2 (stashed), B2, F1 (stashed), B1
-      ctl.prog[n++] = th::SEG_FWD0;
+    for (int k = 0; k < n_steps; ++k) {   // [F1',] F2 (stashed), B2, F1 (stashed), B1
+      if (!use_mid) ctl.prog[n++] = th::SEG_FWD0;
       ctl.prog[n++] = th::SEG_FWD0;
       ctl.prog[n++] = th::SEG_BWD0;
       ctl.prog[n++] = th::SEG_FWD0;
@@ -424,8 +490,6 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
     ctl.prog_len = (uint32_t)n;
     T.gmax = 0u;
   }
-  for (int i = tid; i < 256; i += blockDim.x) reinterpret_cast<unsigned short*>(T.ones)[i] = 0x3C00u;   // FP16 1.0
-  th::fence_async_smem();
   __syncthreads();
   if (warp == th::kIssuerWarp) T.iss.init(ctl, ring, kStages);
   __syncthreads();
@@ -444,7 +508,8 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
   // evaluation and one of the backward tile evaluation (instruction-cache footprint); the small
   // per-sample glue around them is selected by `kind`.
   enum { K_FWD_A = 0, K_FWD_B, K_REV_A0, K_REV_B, K_BWD2, K_REV_A, K_BWD1 };
-  const int n_ops = 2 * (n_steps - 1) + 5 * n_steps;
+  const int rk = use_mid ? 4 : 5;   // evaluations per reverse step
+  const int n_ops = 2 * (n_steps - 1) + rk * n_steps;
 
   for (;;) {
     while (qc < NVFI_TM && !exhausted) {
@@ -480,6 +545,7 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
     }
     if (qc == 0) break;
     __syncthreads();
+    NVFI_TLH(0, 0);
     const int n = min(NVFI_TM, qc);
     const int start = qc - n;
     qc = start;
@@ -507,7 +573,9 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
       for (int a = 0; a < 3; ++a) {
         T.x0[a][tid] = xn[a];
         T.gbar[a][tid] = live ? D.g_x_adv[gi * 3 + a] : 0.f;
+        if (use_mid) T.xm[a][tid] = live ? B.x_mid[gi * 3 + a] : 0.f;
       }
+      T.gate0[tid] = gate_outside(F, xn[0], xn[1], xn[2]);
     }
     __syncthreads();
 
@@ -519,8 +587,8 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
         kind = K_FWD_A + (op & 1);
       } else {                        // reverse sweep
         const int r = op - 2 * (n_steps - 1);
-        k = n_steps - 1 - r / 5;
-        kind = K_REV_A0 + r % 5;
+        k = n_steps - 1 - r / rk;
+        kind = K_REV_A0 + (5 - rk) + r % rk;
       }
       const float dt = sched_dt[k], tcur = sched_t[k], hdt = 0.5f * dt;
       const float tmid = __fsub_rn(tcur, hdt);
@@ -542,12 +610,14 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
       const float* ys = at_mid ? T.xm[1] : T.x0[1];
       const float* zs = at_mid ? T.xm[2] : T.x0[2];
       if (kind == K_BWD2 || kind == K_BWD1) {
-        bwd_eval_h(ctl, T.iss, T, tA, tG, D, stash_a, stash_s, xs, ys, zs, dphase, wphase, aphase, acc_head,
+        // a stashed evaluation leaves A_4 in tile 1 (ping-pong, mlp_h.cuh): tile 1 is the activation tile of
+        // the backward evaluation, tile 0 its gradient tile
+        bwd_eval_h(ctl, T.iss, T, tG, tA, D, stash_a, stash_s, part, xs, ys, zs, dphase, wphase, aphase, acc_head,
                    acc_bias);
       } else {
         float* wout = at_mid ? &T.w1[0][0] : &T.w0[0][0];
         const bool st = (kind == K_REV_B || kind == K_REV_A);
-        th::vel_net_tile_h<ACT_SILU>(ctl, T.iss, 0, wout, xs, ys, zs, T.tvec, tA, dphase, kphase,
+        th::vel_net_tile_h<ACT_SILU>(ctl, T.iss, 0, wout, xs, ys, zs, T.tvec, tA, dphase, kphase, st ? tG : 0u,
                                      st ? stash_a : nullptr, st ? stash_s : nullptr);
       }
       // ---- glue after the evaluation
@@ -594,16 +664,30 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
             T.gm[1][m] = gxe[1];
             T.gm[2][m] = gxe[2];
           }
-        } else if (kind == K_BWD2) {   // adjoint of m = x0 - dt/2 v0(x0)
-          float gmv[3];
+        } else if (kind == K_BWD2) {   // adjoint of m = x0 - dt/2 v0(x0): the upstream gradient of evaluation 1
+          float gmv[3];                // (it does not depend on w0, which the stashed evaluation that follows recomputes)
 #pragma unroll
-          for (int a = 0; a < 3; ++a) gmv[a] = T.gm[a][m] + T.gout[a][m];
-          float gx0[3] = {T.gbar[0][m] + gmv[0], T.gbar[1][m] + gmv[1], T.gbar[2][m] + gmv[2]};
+          for (int a = 0; a < 3; ++a) {
+            gmv[a] = T.gm[a][m] + T.gout[a][m];
+            T.gm[a][m] = gmv[a];
+          }
           float gw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           if (!T.gate0[m]) {
-            const float w[6] = {T.w0[0][m], T.w0[1][m], T.w0[2][m], T.w0[3][m], T.w0[4][m], T.w0[5][m]};
+            const float w[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const float gv[3] = {-hdt * gmv[0], -hdt * gmv[1], -hdt * gmv[2]};
             float gxe[3];
+            basis_bwd(w, T.x0[0][m], T.x0[1][m], T.x0[2][m], gv, gw, gxe);
+          }
+#pragma unroll
+          for (int i = 0; i < 6; ++i) T.gout[i][m] = gw[i];
+        } else if (kind == K_BWD1) {   // dL/dx0 = g + g_m + explicit part of v0's basis + network-input part
+          float gx0[3];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) gx0[a] = T.gbar[a][m] + T.gm[a][m] + T.gout[a][m];
+          if (!T.gate0[m]) {
+            const float w[6] = {T.w0[0][m], T.w0[1][m], T.w0[2][m], T.w0[3][m], T.w0[4][m], T.w0[5][m]};
+            const float gv[3] = {-hdt * T.gm[0][m], -hdt * T.gm[1][m], -hdt * T.gm[2][m]};
+            float gw[6], gxe[3];
             basis_bwd(w, T.x0[0][m], T.x0[1][m], T.x0[2][m], gv, gw, gxe);
             gx0[0] += gxe[0];
             gx0[1] += gxe[1];
@@ -612,11 +696,6 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
           T.gbar[0][m] = gx0[0];
           T.gbar[1][m] = gx0[1];
           T.gbar[2][m] = gx0[2];
-#pragma unroll
-          for (int i = 0; i < 6; ++i) T.gout[i][m] = gw[i];
-        } else if (kind == K_BWD1) {
-#pragma unroll
-          for (int a = 0; a < 3; ++a) T.gbar[a][m] += T.gout[a][m];
         }
       }
       __syncthreads();
@@ -625,23 +704,52 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
   if (tid < NVFI_TM) {
 #pragma unroll
     for (int n2 = 0; n2 < 6; ++n2) red_add(D.g_vel_w[5] + tid * 8 + n2, acc_head[n2]);
+  }
+  if (tid < NT) {   // bias partials: this thread's column over its warp's rows, summed over all tiles
+    const int col = 32 * (lane >> 3) + 8 * (warp >> 2) + (lane & 7);
 #pragma unroll
-    for (int l = 0; l < 5; ++l) red_add(D.g_vel_b[l] + tid, acc_bias[l]);
+    for (int l = 0; l < 5; ++l) red_add(D.g_vel_b[l] + col, acc_bias[l]);
   }
   if (warp < 6) {
     const float s5 = warp_sum(acc_bias[5]);
     if (lane == 0) red_add(D.g_vel_b[5] + warp, s5);
   }
-  if (warp == th::kIssuerWarp && tc::elect_one()) th::bulk_wait0();   // outstanding bulk reductions
+  if (warp == th::kIssuerWarp && tc::elect_one()) th::bulk_wait0();   // outstanding bulk copies
   th::teardown(ctl, T.iss, kTmemCols);
   if (tid == 0 && n_done)
     atomicAdd(reinterpret_cast<unsigned long long*>(B.counters + 10), n_done);
+}
+
+// g_vel_w[l] += sum over the CTAs' private partials (same packed layout)
+__global__ void k_reduce_part(const float* __restrict__ ws, int n_cta, NvfiRenderGrads D) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= kPartF) return;
+  float s = 0.f;
+  for (int c = 0; c < n_cta; ++c)
+    s += *reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(ws) +
+                                         (size_t)c * WS_CTA_F * sizeof(float) + kWsPart + (size_t)e * sizeof(float));
+  const int l = e < 32 * NVFI_TM ? 0 : 1 + (e - 32 * NVFI_TM) / (NVFI_TM * NVFI_TM);
+  D.g_vel_w[l][e - part_off(l)] += s;
 }
 
 }  // namespace thb
 }  // namespace nvfi
 
 using namespace nvfi;
+
+// development aid (called by nvfi_debug_timeline)
+extern "C" int nvfi_debug_timeline_h(long long* dev_buf, int cap) {
+#ifdef NVFI_TIMELINE
+  const int zero[2] = {0, 0};
+  NVFI_CUDA_OK(cudaMemcpyToSymbol(g_tlh_buf, &dev_buf, sizeof(dev_buf)));
+  NVFI_CUDA_OK(cudaMemcpyToSymbol(g_tlh_cap, &cap, sizeof(cap)));
+  NVFI_CUDA_OK(cudaMemcpyToSymbol(g_tlh_n, zero, sizeof(zero)));
+#else
+  (void)dev_buf;
+  (void)cap;
+#endif
+  return NVFI_OK;
+}
 
 extern "C" int nvfi_launch_advect_bwd_h(const NvfiField* F, const NvfiRenderArgs* A, const NvfiRenderBuffers* B,
                                         const NvfiRenderGrads* D, int S, long long total, int sms, cudaStream_t st) {
@@ -660,5 +768,7 @@ extern "C" int nvfi_launch_advect_bwd_h(const NvfiField* F, const NvfiRenderArgs
   const int n_batches = (int)((total + per_batch - 1) / per_batch);
   const int grid = n_batches < sms ? n_batches : sms;
   NVFI_LAUNCH(thb::k_advect_bwd_h, grid, th::kLaunchThreads, smem, st, *F, *A, *B, *D, S, total, n_batches, subs);
+  NVFI_CUDA_OK(cudaGetLastError());
+  NVFI_LAUNCH(thb::k_reduce_part, (thb::kPartF + 255) / 256, 256, 0, st, D->workspace, grid, *D);
   return (int)cudaGetLastError();
 }

@@ -827,10 +827,13 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
 
 using namespace nvfi;
 
+extern "C" int nvfi_get_mlp_mode(void);
 static_assert(tcb::TW_TOTAL <= WS_CTA_F, "per-CTA workspace of the tensor-core backward exceeds WS_CTA_F");
 
+extern "C" int nvfi_debug_timeline_h(long long* dev_buf, int cap);
 extern "C" int nvfi_debug_timeline(long long* dev_buf, int cap) {
   const int zero = 0;
+  if (nvfi_get_mlp_mode() == NVFI_MLP_F16X3) return nvfi_debug_timeline_h(dev_buf, cap);
   NVFI_CUDA_OK(cudaMemcpyToSymbol(tcb::g_tl_buf, &dev_buf, sizeof(dev_buf)));
   NVFI_CUDA_OK(cudaMemcpyToSymbol(tcb::g_tl_cap, &cap, sizeof(cap)));
   NVFI_CUDA_OK(cudaMemcpyToSymbol(tcb::g_tl_n, &zero, sizeof(zero)));

@@ -29,6 +29,12 @@
 
 #include "mlp_tc.cuh"
 
+// Development aid (tools/probe_timeline.py): a translation unit may define NVFI_TLH(tag, who) to record
+// (tag, clock64) pairs at the phase boundaries; compiled out otherwise.
+#ifndef NVFI_TLH
+#define NVFI_TLH(tag, who)
+#endif
+
 namespace nvfi {
 namespace th {
 
@@ -84,6 +90,7 @@ __device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, uint32_t ssrc, 
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // two floats -> packed FP16 pair (element `a` at the lower address), saturating to the finite range
@@ -280,11 +287,11 @@ __device__ inline void teardown(C& c, Issuer& is, uint32_t tmem_cols) {
 // Issuer warp: the MMAs of 32-column group g (2 K steps of 16) of a forward `layer` whose A operand is the
 // tile at `tile_u32`, into accumulator D[layer & 1].  Even groups acquire a K block of the ring, odd
 // groups (and the single group of layer 0) release it.  With wait_store the elected thread first waits
-// until its outstanding bulk stores have read their shared-memory source, with commit_d the accumulator
-// is published on dbar.
+// until its outstanding bulk stores (1: all, 2: all but the newest) have read their shared-memory source,
+// with commit_d the accumulator is published on dbar.
 template <class C>
 __device__ __forceinline__ void issue_group(C& c, Issuer& is, uint32_t tile_u32, int layer, uint32_t g,
-                                            uint32_t& stage_u32, bool commit_d, bool wait_store) {
+                                            uint32_t& stage_u32, bool commit_d, int wait_store) {
   const uint32_t n = (layer == NVFI_VEL_LAYERS - 1) ? 16u : 128u;
   const uint32_t idesc = idesc_f16((int)n);
   if ((g & 1u) == 0u) stage_u32 = ring_acquire(c, is);
@@ -303,7 +310,8 @@ __device__ __forceinline__ void issue_group(C& c, Issuer& is, uint32_t tile_u32,
       mma_f16_ss(d, a_hi + o, kDescHiSw128, w_lo + o, kDescHiSw128, idesc, 1u);
     }
     if (release) tc::tc_commit(&c.empty[is.c_stage]);
-    if (wait_store) bulk_wait_read0();
+    if (wait_store == 1) bulk_wait_read0();        // all bulk stores have read their source
+    else if (wait_store == 2) bulk_wait_read1();   // all but the most recent one
     if (commit_d) tc::tc_commit(&c.dbar);
   }
   __syncwarp();
@@ -327,25 +335,35 @@ __device__ __forceinline__ float act_h(float x, float& da) {
 
 // Stash of one stashed evaluation (global memory, per CTA), for the backward pass:
 //   stash_a: [enc: hi slab 0 (16 KB) | lo slab 0 (16 KB)] [A_0 .. A_3: 4 x 64 KB tile images]
-//   stash_s: S_l[unit][sample] = act'(h_l), l = 0..4 (FP32, unit-major: a warp stores 128 contiguous bytes)
+//   stash_s: S_l[unit / 4][sample][unit % 4] = act'(h_l), l = 0..4 (FP32; a thread owns 16-byte quads of units,
+//            a warp stores / loads 512 contiguous bytes per instruction)
 constexpr size_t kStashABytes = 32768 + 4 * (size_t)kTileBytes;
 constexpr size_t kStashSFloats = 5 * (size_t)NVFI_TM * NVFI_TM;
 
 // Weight net of VelBasis on a tile (models/velocity_field.py:58-67, models/base_network.py:42-54):
 // inputs (x,y,z,t)[m] in shared memory, outputs outS[0..5][m].  `tile_u32`: shared-window address of the
-// 64 KB activation tile (1024-aligned); on return it holds A_4 = act(h_4).  Whole CTA (2 block barriers).
+// 64 KB activation tile (1024-aligned); the epilogue of layer l writes A_l over A_{l-1} in place and on
+// return the tile holds A_4 = act(h_4).  With a second tile (tile1_u32 != 0: the stashed evaluations of the
+// backward kernel) the layers ping-pong instead — the encoding and A_1, A_3 in tile 0; A_0, A_2, A_4 in
+// tile 1 — so that the bulk copy of A_l to the stash has a whole layer to read its tile before the tile
+// is overwritten.  Whole CTA (2 block barriers).
 template <int ACT, class C>
 __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, const float* xs,
                                const float* ys, const float* zs, const float* ts, uint32_t tile_u32,
-                               uint32_t& dphase, uint32_t& kphase, unsigned char* __restrict__ stash_a = nullptr,
+                               uint32_t& dphase, uint32_t& kphase, uint32_t tile1_u32 = 0u,
+                               unsigned char* __restrict__ stash_a = nullptr,
                                float* __restrict__ stash_s = nullptr) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool stash = stash_a != nullptr;
+  if (tile1_u32 == 0u) tile1_u32 = tile_u32;
+  // layer L reads tile (L & 1), its epilogue writes tile ((L + 1) & 1)
   if (warp == kIssuerWarp) {      // ---- issuer warp: all 32 lanes run the issue code uniformly
     Issuer is = is_ref;
+    NVFI_TLH(1010, 1);
     ring_top_up(c, is);           // weights stream in while the workers encode
     __syncthreads();              // (1) the encoding (group 0 of layer 0's A operand) is in the tile
     tc::tc_fence_after();
+    NVFI_TLH(1011, 1);
     uint32_t stage = 0;
     if (stash && tc::elect_one()) {
       bulk_s2g(stash_a, tile_u32, kSlab);
@@ -353,7 +371,7 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
       bulk_commit();
     }
     __syncwarp();
-    issue_group(c, is, tile_u32, 0, 0, stage, true, stash);
+    issue_group(c, is, tile_u32, 0, 0, stage, true, (stash && tile1_u32 == tile_u32) ? 1 : 0);
 #pragma unroll 1
     for (int l = 0; l < NVFI_VEL_LAYERS - 1; ++l) {
 #pragma unroll 1
@@ -363,11 +381,15 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
         tc::tc_fence_after();
         const bool st = stash && l < 4 && g == 3;
         if (st && tc::elect_one()) {   // A_l is complete: copy the tile image to the stash
-          bulk_s2g(stash_a + 32768 + (size_t)l * kTileBytes, tile_u32, kTileBytes);
+          bulk_s2g(stash_a + 32768 + (size_t)l * kTileBytes, ((l + 1) & 1) ? tile1_u32 : tile_u32, kTileBytes);
           bulk_commit();
         }
         __syncwarp();
-        issue_group(c, is, tile_u32, l + 1, g, stage, g == 3, st);
+        // before layer l + 1's accumulator is published its epilogue's target tile must be free: in place
+        // that is the tile just copied (wait for it), with two tiles it is the copy issued a layer ago
+        issue_group(c, is, ((l + 1) & 1) ? tile1_u32 : tile_u32, l + 1, g, stage, g == 3,
+                    (stash && g == 3) ? (tile1_u32 == tile_u32 ? 1 : 2) : 0);
+        NVFI_TLH(1020 + 4 * l + (int)g, 1);
       }
       ++kphase;
     }
@@ -380,7 +402,8 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
   const int m = q * 32 + lane;                 // sample (= TMEM lane = tile row) of this thread
   const uint32_t tb = c.tmem_base;
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-  const uint32_t row_u32 = tile_u32 + (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);
+  const uint32_t row_off = (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);
+  const uint32_t row_u32 = tile_u32 + row_off;
   const uint32_t x7 = (uint32_t)(m & 7);
 
   // ---- PositionEncoder(3) of (x, y, z, t): 28 values + 4 zeros into columns [0, 32):
@@ -406,7 +429,9 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
     fence_async_smem();
   }
   tc::tc_fence_before();
+  NVFI_TLH(10, 0);
   __syncthreads();   // (1)
+  NVFI_TLH(11, 0);
 
 #pragma unroll 1
   for (int l = 0; l < NVFI_VEL_LAYERS - 1; ++l) {
@@ -414,6 +439,7 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
     tc::mbar_wait(&c.dbar, dphase & 1);
     ++dphase;
     tc::tc_fence_after();
+    NVFI_TLH(20 + l, 0);
     const uint32_t dcol = tb + lane_base + kColD + 128u * (uint32_t)(l & 1) + (uint32_t)(h * 8);
     uint32_t raw[4][8];
 #pragma unroll
@@ -429,14 +455,15 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
       float av[8], sv[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) av[i] = act_h<ACT>(__uint_as_float(raw[g][i]) + bb[i], sv[i]);
-      if (stash) {   // unit-major: a warp stores 128 contiguous bytes per unit
-        float* sp = stash_s + ((size_t)l * NVFI_TM + col) * NVFI_TM + m;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) __stcg(sp + (size_t)i * NVFI_TM, sv[i]);
+      if (stash) {   // quads of units: a warp stores 512 contiguous bytes per quad
+        float4* sp = reinterpret_cast<float4*>(stash_s) + ((size_t)l * 32 + (col >> 2)) * NVFI_TM + m;
+        __stcg(sp, make_float4(sv[0], sv[1], sv[2], sv[3]));
+        __stcg(sp + NVFI_TM, make_float4(sv[4], sv[5], sv[6], sv[7]));
       }
       uint4 hi, lo;
       split8(av, hi, lo);
-      const uint32_t a = row_u32 + (uint32_t)(g >> 1) * kSlab + ((((uint32_t)(4 * g + h) & 7u) ^ x7) << 4);
+      const uint32_t a = (((l + 1) & 1) ? tile1_u32 : tile_u32) + row_off + (uint32_t)(g >> 1) * kSlab +
+                         ((((uint32_t)(4 * g + h) & 7u) ^ x7) << 4);
       st_shared_v4(a, hi);
       st_shared_v4(a + kLoOff, lo);
       fence_async_smem();
@@ -445,11 +472,13 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
       if (lane == 0) tc::mbar_arrive(&c.kready[g]);
     }
     ++kphase;
+    NVFI_TLH(30 + l, 0);
   }
   // ---- head: 6 basis weights
   tc::mbar_wait(&c.dbar, dphase & 1);
   ++dphase;
   tc::tc_fence_after();
+  NVFI_TLH(40, 0);
   if (h == 0) {
     uint32_t raw[8];
     tc::tmem_ld8_nowait(tb + lane_base + kColD + 128u * (uint32_t)((NVFI_VEL_LAYERS - 1) & 1), raw);

@@ -244,6 +244,11 @@ __device__ __forceinline__ void sample_advect_body(const NvfiField& F, const Nvf
       B.x_adv[gi * 3 + 0] = sm.tile.x[0][tid];
       B.x_adv[gi * 3 + 1] = sm.tile.x[1][tid];
       B.x_adv[gi * 3 + 2] = sm.tile.x[2][tid];
+      if (B.x_mid != nullptr) {   // midpoint of the last RK2 step, for the backward pass
+        B.x_mid[gi * 3 + 0] = sm.tile.xm[0][tid];
+        B.x_mid[gi * 3 + 1] = sm.tile.xm[1][tid];
+        B.x_mid[gi * 3 + 2] = sm.tile.xm[2][tid];
+      }
     }
     __syncthreads();
   }

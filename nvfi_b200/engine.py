@@ -353,7 +353,7 @@ def time_plan(field, t, transfer_vel: bool) -> Tuple[float, float, float, bool]:
 
 class RenderOutputs:
     __slots__ = ("rgb_map", "depth_map", "acc_map", "weights", "mask_map", "x_adv", "valid", "rgb",
-                 "sigma", "chunk_inside", "counters", "stats", "args", "keep")
+                 "sigma", "chunk_inside", "counters", "stats", "args", "keep", "x_mid")
 
 
 def render_forward(binding: FieldBinding, rays_o: torch.Tensor, rays_d: torch.Tensor, t, *,
@@ -385,6 +385,8 @@ def render_forward(binding: FieldBinding, rays_o: torch.Tensor, rays_d: torch.Te
     o.valid = torch.empty(n, S, device=dev, dtype=torch.uint8)
     o.rgb = torch.empty(n, S, 3, **f32)
     o.sigma = torch.empty(n, S, **f32) if save_sigma else None
+    # RK2 midpoints for the backward pass (training renders that advect)
+    o.x_mid = torch.empty(n, S, 3, **f32) if (save_sigma and advect) else None
     o.chunk_inside = torch.empty(n_chunks, device=dev, dtype=torch.uint8)
     o.counters = torch.empty(16, device=dev, dtype=torch.int32)
     o.stats = torch.empty(4, device=dev, dtype=torch.int64) if want_stats else None
@@ -421,6 +423,7 @@ def render_forward(binding: FieldBinding, rays_o: torch.Tensor, rays_d: torch.Te
     b.x_adv, b.valid, b.rgb = o.x_adv.data_ptr(), o.valid.data_ptr(), o.rgb.data_ptr()
     b.sigma = _ptr(o.sigma)
     b.chunk_inside, b.counters, b.stats = o.chunk_inside.data_ptr(), o.counters.data_ptr(), _ptr(o.stats)
+    b.x_mid = _ptr(o.x_mid)
     L.check(lib.nvfi_render_forward(C.byref(s), C.byref(a), C.byref(b), _stream()), "render_forward")
     o.args = (a, b)
     o.keep = (rays_o, rays_d, jitter, chunk_bg)

@@ -1,0 +1,23 @@
+#!/usr/bin/env python
+""""Install" the unmodified reference for the CPU arm of bench.py: copy its pure-Python packages
+(models/, utils/, config/) from the read-only checkout into baseline/_ref/ (git-ignored; shipped to the
+GPU box by gpurun).  The reference has no setup.py / pyproject, so pip has nothing to build:
+
+    python tools/install_reference.py [/root/reference]
+"""
+import os
+import shutil
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+src = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+dst = os.path.join(ROOT, "baseline", "_ref")
+if not os.path.isfile(os.path.join(src, "models", "nvfi.py")):
+    sys.exit(f"no reference checkout at {src}")
+os.makedirs(dst, exist_ok=True)
+for d in ("models", "utils", "config"):
+    t = os.path.join(dst, d)
+    if os.path.exists(t):
+        shutil.rmtree(t)
+    shutil.copytree(os.path.join(src, d), t, ignore=shutil.ignore_patterns("__pycache__", "*.pyc", ".DS_Store"))
+print("installed", sorted(os.listdir(dst)), "->", dst)

@@ -20,22 +20,28 @@ def step():
     rgb, *_ = f.render_rays(0.33, o, d, white_bg=True, ray_chunk=2048, jitter=jit)
     torch.nn.functional.mse_loss(rgb, target).backward()
 step(); torch.cuda.synchronize()
-buf = torch.zeros(20000, dtype=torch.int64, device="cuda")
+buf = torch.zeros(40000, dtype=torch.int64, device="cuda")
 lib.nvfi_debug_timeline(buf.data_ptr(), buf.numel())
 step(); torch.cuda.synchronize()
 lib.nvfi_debug_timeline(None, 0)
 b = buf.cpu().tolist()
-ev = [(b[i], b[i + 1]) for i in range(0, len(b), 2) if b[i + 1] != 0]
-print("events", len(ev))
-# per-transition statistics over tiles 2.. (skip warm-up)
-d = collections.defaultdict(list)
-for (t0, c0), (t1, c1) in zip(ev, ev[1:]):
-    d[(t0, t1)].append(c1 - c0)
-tot = 0
-for k in sorted(d, key=lambda k: -sum(d[k])):
-    v = d[k]; tot += sum(v)
-for k in sorted(d, key=lambda k: -sum(d[k]))[:40]:
-    v = d[k]
-    print(f"{k[0]:4d}->{k[1]:4d}  n={len(v):4d} mean {sum(v)/len(v):9.0f} cyc  share {100*sum(v)/tot:5.1f}%")
-tiles = [c for t, c in ev if t == 0]
-if len(tiles) > 2: print("cycles per tile", (tiles[-1] - tiles[1]) / (len(tiles) - 2))
+half = len(b) // 2
+h16 = lib.nvfi_get_mlp_mode() == L.MLP_F16X3
+parts = [("worker thread 0", b[:half]), ("issuer warp", b[half:])] if h16 else [("thread 0", b)]
+for who, bb in parts:
+    ev = [(bb[i], bb[i + 1]) for i in range(0, len(bb), 2) if bb[i + 1] != 0]
+    print(f"== {who}: {len(ev)} events")
+    if len(ev) < 3:
+        continue
+    # skip the first tile (warm-up)
+    starts = [i for i, (t, c) in enumerate(ev) if t == (0 if who != "issuer warp" else ev[0][0])]
+    d = collections.defaultdict(list)
+    for (t0, c0), (t1, c1) in zip(ev, ev[1:]):
+        d[(t0, t1)].append(c1 - c0)
+    tot = sum(sum(v) for v in d.values())
+    for k in sorted(d, key=lambda k: -sum(d[k]))[:45]:
+        v = d[k]
+        print(f"{k[0]:5d}->{k[1]:5d}  n={len(v):4d} mean {sum(v)/len(v):9.0f} cyc  share {100*sum(v)/tot:5.1f}%")
+    tiles = [c for t, c in ev if t == 0]
+    if len(tiles) > 2:
+        print("cycles per tile", (tiles[-1] - tiles[1]) / (len(tiles) - 2))
