@@ -401,16 +401,14 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
     //      part[k][n]: plain read-modify-write of addresses only this thread ever touches, 128 contiguous
     //      bytes per warp instruction; it overlaps the next layer's MMAs (D1 ping-pongs in tensor memory)
     if (L > 0 || h == 0) {
-      float* pp = part + part_off(L) + (size_t)(h * 32) * NVFI_TM + m;
+      // coalesced fire-and-forget reductions: one 128-byte line of the packed gradient per warp instruction
+      float* pp = D.g_vel_w[L] + (size_t)(h * 32) * NVFI_TM + m;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        float old[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) old[i] = ldcg_f(pp + (size_t)(half * 16 + i) * NVFI_TM);
         float dv[16];
         tc::tmem_ld16(tb + lane_base + kColD1 + 128u * (uint32_t)(L & 1) + (uint32_t)(h * 32 + half * 16), dv);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) __stcg(pp + (size_t)(half * 16 + i) * NVFI_TM, fmaf(dv[i], inv_scale, old[i]));
+        for (int i = 0; i < 16; ++i) red_add(pp + (size_t)(half * 16 + i) * NVFI_TM, dv[i] * inv_scale);
       }
     }
     tc::tc_fence_before();   // the D1 reads are ordered before the next barrier (the issuer reuses D1 two layers on)
@@ -452,8 +450,7 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
   float* stash_s = reinterpret_cast<float*>(ws + kWsStashS);
   float* xsteps = reinterpret_cast<float*>(ws + kWsXsteps);
   float* part = reinterpret_cast<float*>(ws + kWsPart);
-  for (int i = threadIdx.x; i < kPartF / 4; i += blockDim.x)   // the CTA's partial weight gradients start at zero
-    reinterpret_cast<float4*>(part)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // uniform RK2 schedule of this render call (models/tensorf_keyframe.py:577-609)
   float sched_dt[MAX_RK2_STEPS], sched_t[MAX_RK2_STEPS];
@@ -769,6 +766,5 @@ extern "C" int nvfi_launch_advect_bwd_h(const NvfiField* F, const NvfiRenderArgs
   const int grid = n_batches < sms ? n_batches : sms;
   NVFI_LAUNCH(thb::k_advect_bwd_h, grid, th::kLaunchThreads, smem, st, *F, *A, *B, *D, S, total, n_batches, subs);
   NVFI_CUDA_OK(cudaGetLastError());
-  NVFI_LAUNCH(thb::k_reduce_part, (thb::kPartF + 255) / 256, 256, 0, st, D->workspace, grid, *D);
   return (int)cudaGetLastError();
 }
