@@ -14,11 +14,17 @@
 // A_{l-1} (tile T_A, TMA-loaded from the stash), per layer l = 4..0:
 //     dX:  D0[m][k] = sum_n G_l[m][n] W_l[n][k]        A = T_G K-major,  B = W_l^T image (ring)
 //     dW:  D1[n][k] = sum_m G_l[m][n] A_{l-1}[m][k]    A = T_G MN-major, B = T_A MN-major  (same bytes!)
-//     db:  Db[n][.] = sum_m G_l[m][n] * 1              A = T_G MN-major, B = a constant block of ones
-//     G_{l-1} = D0 (.) S_{l-1} -> T_G (FP16 split);    D1 -> transposed into T_A -> ONE 64 KB
-//     cp.reduce.async.bulk (.add.f32) into the packed weight gradient; Db -> registers.
+//     G_{l-1} = D0 (.) S_{l-1} -> T_G (FP16 split)
+//     dW flush: the accumulator lane IS the output unit n, and the packed gradient is [k][n], so the
+//     32 threads of a warp add 128 contiguous bytes per red.global.add instruction (coalesced,
+//     fire-and-forget; D1 ping-pongs in tensor memory so the flush runs under the next layer's MMAs)
+//     db: column sums of G_{l-1} by a register butterfly in the epilogue (FP32, before the split)
 // No operand is ever transposed by a thread: FP16 tiles can be read K-major and MN-major.
 // The head (128 -> 6) is two small MMAs against a [128][16] tile of the upstream gradient.
+// Tried and rejected on the bench workload (all parity-green): TMA bulk reduce-add of D1 staged in T_A
+// (353 ms: the staging tile, the reduction's read and the next A_{l-2} load serialise), per-CTA private
+// partials with plain read-modify-write (291 ms: two exposed L2 round trips per layer), constant-ones
+// MMAs for the bias sums (16 tiny MMAs per layer cost ~650 cycles of tensor time).
 //
 // FP16 range: the upstream gradient of a tile is scaled by a power of two so that its largest
 // component is in [8, 16) (12 binades of headroom for growth through the layers, 2^-29 of the tile
@@ -59,11 +65,7 @@ constexpr uint32_t kColDh = 384;            // head weight gradient (16 columns;
 constexpr size_t kWsStashA = 0;
 constexpr size_t kWsStashS = th::kStashABytes;
 constexpr size_t kWsXsteps = kWsStashS + th::kStashSFloats * sizeof(float);
-constexpr size_t kWsPart = kWsXsteps + (size_t)MAX_RK2_STEPS * 3 * NVFI_TM * sizeof(float);
-// per-CTA partial weight gradients in the packed (k_pad, n_pad) layout: layer 0 (32 x 128), layers 1..4
-constexpr int kPartF = 32 * NVFI_TM + 4 * NVFI_TM * NVFI_TM;
-__host__ __device__ constexpr int part_off(int l) { return l == 0 ? 0 : 32 * NVFI_TM + (l - 1) * NVFI_TM * NVFI_TM; }
-constexpr size_t kWsBytes = kWsPart + (size_t)kPartF * sizeof(float);
+constexpr size_t kWsBytes = kWsXsteps + (size_t)MAX_RK2_STEPS * 3 * NVFI_TM * sizeof(float);
 static_assert(kWsBytes <= (size_t)WS_CTA_F * sizeof(float), "per-CTA workspace of k_advect_bwd_h exceeds WS_CTA_F");
 
 struct BwdTile {
@@ -90,11 +92,6 @@ struct BwdTile {
 __device__ __forceinline__ float4 ldcg4_now(const float4* p) {
   float4 v;
   asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ float ldcg_f(const float* p) {
-  float v;
-  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ void red_add(float* p, float v) {
@@ -128,9 +125,9 @@ __device__ __forceinline__ float colsum8(const float v[8], int lane) {
 // and head gradients to the register accumulators.  Whole CTA (13 block barriers).
 __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint32_t tA, uint32_t tG,
                            const NvfiRenderGrads& D, const unsigned char* __restrict__ stash_a,
-                           const float* __restrict__ stash_s, float* __restrict__ part, const float* xs,
-                           const float* ys, const float* zs, uint32_t& dphase, uint32_t& wphase, uint32_t& aphase,
-                           float (&acc_head)[6], float (&acc_bias)[6]) {
+                           const float* __restrict__ stash_s, const float* xs, const float* ys, const float* zs,
+                           uint32_t& dphase, uint32_t& wphase, uint32_t& aphase, float (&acc_head)[6],
+                           float (&acc_bias)[6]) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t gw_hi = tc::smem_u32(T.gw_hi), gw_lo = tc::smem_u32(T.gw_lo);
 
@@ -397,9 +394,8 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
       }
       continue;
     }
-    // ---- D1[n][k] (this thread: n = m, k = 32 h + i) is added to the CTA's private partial gradient
-    //      part[k][n]: plain read-modify-write of addresses only this thread ever touches, 128 contiguous
-    //      bytes per warp instruction; it overlaps the next layer's MMAs (D1 ping-pongs in tensor memory)
+    // ---- D1[n][k] (this thread: n = m, k = 32 h + i) is added to the packed gradient [k][n]; the flush
+    //      overlaps the next layer's MMAs (D1 ping-pongs in tensor memory)
     if (L > 0 || h == 0) {
       // coalesced fire-and-forget reductions: one 128-byte line of the packed gradient per warp instruction
       float* pp = D.g_vel_w[L] + (size_t)(h * 32) * NVFI_TM + m;
@@ -449,8 +445,6 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
   unsigned char* stash_a = ws + kWsStashA;
   float* stash_s = reinterpret_cast<float*>(ws + kWsStashS);
   float* xsteps = reinterpret_cast<float*>(ws + kWsXsteps);
-  float* part = reinterpret_cast<float*>(ws + kWsPart);
-
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // uniform RK2 schedule of this render call (models/tensorf_keyframe.py:577-609)
   float sched_dt[MAX_RK2_STEPS], sched_t[MAX_RK2_STEPS];
@@ -609,12 +603,12 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
       if (kind == K_BWD2 || kind == K_BWD1) {
         // a stashed evaluation leaves A_4 in tile 1 (ping-pong, mlp_h.cuh): tile 1 is the activation tile of
         // the backward evaluation, tile 0 its gradient tile
-        bwd_eval_h(ctl, T.iss, T, tG, tA, D, stash_a, stash_s, part, xs, ys, zs, dphase, wphase, aphase, acc_head,
+        bwd_eval_h(ctl, T.iss, T, tG, tA, D, stash_a, stash_s, xs, ys, zs, dphase, wphase, aphase, acc_head,
                    acc_bias);
       } else {
         float* wout = at_mid ? &T.w1[0][0] : &T.w0[0][0];
         const bool st = (kind == K_REV_B || kind == K_REV_A);
-        th::vel_net_tile_h<ACT_SILU>(ctl, T.iss, 0, wout, xs, ys, zs, T.tvec, tA, dphase, kphase, st ? tG : 0u,
+        th::vel_net_tile_h<ACT_SILU, false>(ctl, T.iss, 0, wout, xs, ys, zs, T.tvec, tA, dphase, kphase, st ? tG : 0u,
                                      st ? stash_a : nullptr, st ? stash_s : nullptr);
       }
       // ---- glue after the evaluation
@@ -715,18 +709,6 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
   th::teardown(ctl, T.iss, kTmemCols);
   if (tid == 0 && n_done)
     atomicAdd(reinterpret_cast<unsigned long long*>(B.counters + 10), n_done);
-}
-
-// g_vel_w[l] += sum over the CTAs' private partials (same packed layout)
-__global__ void k_reduce_part(const float* __restrict__ ws, int n_cta, NvfiRenderGrads D) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= kPartF) return;
-  float s = 0.f;
-  for (int c = 0; c < n_cta; ++c)
-    s += *reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(ws) +
-                                         (size_t)c * WS_CTA_F * sizeof(float) + kWsPart + (size_t)e * sizeof(float));
-  const int l = e < 32 * NVFI_TM ? 0 : 1 + (e - 32 * NVFI_TM) / (NVFI_TM * NVFI_TM);
-  D.g_vel_w[l][e - part_off(l)] += s;
 }
 
 }  // namespace thb

@@ -47,6 +47,10 @@ constexpr uint32_t kLoOff = 32768;            // lo slabs follow the two hi slab
 constexpr uint32_t kStageBytes = 32768;       // one K block of a 128-row image: hi slab + lo slab
 constexpr int kMaxStages = 4;
 constexpr uint32_t kColD = 0;                 // accumulators D[0] / D[1] at TMEM columns 0 / 128
+// TS form: the A operand (activations / upstream gradient) lives in tensor memory, two FP16 per 32-bit
+// column (low half = even K index; tools/probe_h16.cu test 4): 64 columns of hi halves, 64 of lo halves.
+// Shared memory then only feeds the B operand, which halves the MMAs' shared-memory reads.
+constexpr uint32_t kColAhi = 384, kColAlo = 448;
 enum : uint8_t { SEG_FWD0 = 0, SEG_FWD1 = 1, SEG_BWD0 = 2 };
 
 // high word of a SWIZZLE_128B shared-memory descriptor: SBO = 1024 B, version 1, layout type 2
@@ -75,6 +79,21 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint32_t a_lo, uint3
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(ad), "l"(bd), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+  const uint64_t bd = ((uint64_t)b_hi << 32) | b_lo;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bd), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint4& v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -289,7 +308,7 @@ __device__ inline void teardown(C& c, Issuer& is, uint32_t tmem_cols) {
 // groups (and the single group of layer 0) release it.  With wait_store the elected thread first waits
 // until its outstanding bulk stores (1: all, 2: all but the newest) have read their shared-memory source,
 // with commit_d the accumulator is published on dbar.
-template <class C>
+template <bool TS, class C>
 __device__ __forceinline__ void issue_group(C& c, Issuer& is, uint32_t tile_u32, int layer, uint32_t g,
                                             uint32_t& stage_u32, bool commit_d, int wait_store) {
   const uint32_t n = (layer == NVFI_VEL_LAYERS - 1) ? 16u : 128u;
@@ -305,9 +324,16 @@ __device__ __forceinline__ void issue_group(C& c, Issuer& is, uint32_t tile_u32,
 #pragma unroll
     for (uint32_t ks = 0; ks < 2; ++ks) {
       const uint32_t o = ((g & 1u) * 2u + ks) * 2u;   // 32 bytes per K step, in 16-byte units
-      mma_f16_ss(d, a_hi + o, kDescHiSw128, w_hi + o, kDescHiSw128, idesc, (g | ks) ? 1u : 0u);
-      mma_f16_ss(d, a_lo + o, kDescHiSw128, w_hi + o, kDescHiSw128, idesc, 1u);
-      mma_f16_ss(d, a_hi + o, kDescHiSw128, w_lo + o, kDescHiSw128, idesc, 1u);
+      if (TS) {
+        const uint32_t ta = is.tb + (2u * g + ks) * 8u;   // 8 columns per K step
+        mma_f16_ts(d, ta + kColAhi, w_hi + o, kDescHiSw128, idesc, (g | ks) ? 1u : 0u);
+        mma_f16_ts(d, ta + kColAlo, w_hi + o, kDescHiSw128, idesc, 1u);
+        mma_f16_ts(d, ta + kColAhi, w_lo + o, kDescHiSw128, idesc, 1u);
+      } else {
+        mma_f16_ss(d, a_hi + o, kDescHiSw128, w_hi + o, kDescHiSw128, idesc, (g | ks) ? 1u : 0u);
+        mma_f16_ss(d, a_lo + o, kDescHiSw128, w_hi + o, kDescHiSw128, idesc, 1u);
+        mma_f16_ss(d, a_hi + o, kDescHiSw128, w_lo + o, kDescHiSw128, idesc, 1u);
+      }
     }
     if (release) tc::tc_commit(&c.empty[is.c_stage]);
     if (wait_store == 1) bulk_wait_read0();        // all bulk stores have read their source
@@ -347,7 +373,7 @@ constexpr size_t kStashSFloats = 5 * (size_t)NVFI_TM * NVFI_TM;
 // backward kernel) the layers ping-pong instead — the encoding and A_1, A_3 in tile 0; A_0, A_2, A_4 in
 // tile 1 — so that the bulk copy of A_l to the stash has a whole layer to read its tile before the tile
 // is overwritten.  Whole CTA (2 block barriers).
-template <int ACT, class C>
+template <int ACT, bool TS, class C>
 __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, const float* xs,
                                const float* ys, const float* zs, const float* ts, uint32_t tile_u32,
                                uint32_t& dphase, uint32_t& kphase, uint32_t tile1_u32 = 0u,
@@ -371,7 +397,7 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
       bulk_commit();
     }
     __syncwarp();
-    issue_group(c, is, tile_u32, 0, 0, stage, true, (stash && tile1_u32 == tile_u32) ? 1 : 0);
+    issue_group<TS>(c, is, tile_u32, 0, 0, stage, true, (stash && !TS && tile1_u32 == tile_u32) ? 1 : 0);
 #pragma unroll 1
     for (int l = 0; l < NVFI_VEL_LAYERS - 1; ++l) {
 #pragma unroll 1
@@ -387,7 +413,7 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
         __syncwarp();
         // before layer l + 1's accumulator is published its epilogue's target tile must be free: in place
         // that is the tile just copied (wait for it), with two tiles it is the copy issued a layer ago
-        issue_group(c, is, ((l + 1) & 1) ? tile1_u32 : tile_u32, l + 1, g, stage, g == 3,
+        issue_group<TS>(c, is, ((l + 1) & 1) ? tile1_u32 : tile_u32, l + 1, g, stage, g == 3,
                     (stash && g == 3) ? (tile1_u32 == tile_u32 ? 1 : 2) : 0);
         NVFI_TLH(1020 + 4 * l + (int)g, 1);
       }
@@ -423,10 +449,17 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
     }
     uint4 hi, lo;
     split8(v, hi, lo);
-    const uint32_t a = row_u32 + (((uint32_t)h ^ x7) << 4);
-    st_shared_v4(a, hi);
-    st_shared_v4(a + kLoOff, lo);
-    fence_async_smem();
+    if (TS) {
+      tmem_st4(tb + lane_base + kColAhi + (uint32_t)(4 * h), hi);
+      tmem_st4(tb + lane_base + kColAlo + (uint32_t)(4 * h), lo);
+    }
+    if (!TS || stash) {
+      const uint32_t a = row_u32 + (((uint32_t)h ^ x7) << 4);
+      st_shared_v4(a, hi);
+      st_shared_v4(a + kLoOff, lo);
+      fence_async_smem();
+    }
+    if (TS) tc::tmem_st_wait();
   }
   tc::tc_fence_before();
   NVFI_TLH(10, 0);
@@ -462,11 +495,18 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
       }
       uint4 hi, lo;
       split8(av, hi, lo);
-      const uint32_t a = (((l + 1) & 1) ? tile1_u32 : tile_u32) + row_off + (uint32_t)(g >> 1) * kSlab +
-                         ((((uint32_t)(4 * g + h) & 7u) ^ x7) << 4);
-      st_shared_v4(a, hi);
-      st_shared_v4(a + kLoOff, lo);
-      fence_async_smem();
+      if (TS) {   // next layer's A operand: tensor memory
+        tmem_st4(tb + lane_base + kColAhi + (uint32_t)(16 * g + 4 * h), hi);
+        tmem_st4(tb + lane_base + kColAlo + (uint32_t)(16 * g + 4 * h), lo);
+      }
+      if (!TS || stash) {   // shared-memory tile: the A operand (SS form) / the image copied to the stash
+        const uint32_t a = (((l + 1) & 1) ? tile1_u32 : tile_u32) + row_off + (uint32_t)(g >> 1) * kSlab +
+                           ((((uint32_t)(4 * g + h) & 7u) ^ x7) << 4);
+        st_shared_v4(a, hi);
+        st_shared_v4(a + kLoOff, lo);
+        fence_async_smem();
+      }
+      if (TS) tc::tmem_st_wait();
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&c.kready[g]);

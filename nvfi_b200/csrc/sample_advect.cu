@@ -77,31 +77,31 @@ struct TcMlp {
   }
 };
 
-// FP16-split tensor cores, operands in shared memory (mlp_h.cuh) — the product path
+// FP16-split tensor cores (mlp_h.cuh) — the product path.  TS form: activations in tensor memory, shared
+// memory holds only the weight ring.
 struct HMlp {
   static constexpr int kThreads = th::kThreads;
   static constexpr int kLaunchThreads = th::kLaunchThreads;
   static constexpr int kStages = 4;
-  static constexpr uint32_t kTmemCols = 256;   // D ping-pong
-  static constexpr size_t kBytes = 1024 + th::kTileBytes + (size_t)kStages * th::kStageBytes + sizeof(th::Ctl);
+  static constexpr uint32_t kTmemCols = 512;   // D ping-pong (256) + A operand hi | lo (128)
+  static constexpr size_t kBytes = 1024 + (size_t)kStages * th::kStageBytes + sizeof(th::Ctl);
   th::Ctl* ctl;
   th::Issuer is;
-  uint32_t tile_u32, dphase, kphase;
+  uint32_t dphase, kphase;
   __device__ void init(unsigned char* p, const NvfiLinear* n0, const NvfiLinear* n1, int) {
     const uint32_t a = tc::smem_u32(p);
     p += (1024u - (a & 1023u)) & 1023u;
-    tile_u32 = tc::smem_u32(p);
-    ctl = reinterpret_cast<th::Ctl*>(p + th::kTileBytes + (size_t)kStages * th::kStageBytes);
+    ctl = reinterpret_cast<th::Ctl*>(p + (size_t)kStages * th::kStageBytes);
     dphase = 0;
     kphase = 0;
     th::setup(*ctl, n0, n1, kTmemCols);
-    is.init(*ctl, tile_u32 + th::kTileBytes, kStages);
+    is.init(*ctl, tc::smem_u32(p), kStages);
   }
   __device__ void finish() { th::teardown(*ctl, is, kTmemCols); }
   template <int ACT>
   __device__ void eval(int which, float* outS, const float* xs, const float* ys, const float* zs,
                        const float* ts) {
-    th::vel_net_tile_h<ACT>(*ctl, is, which, outS, xs, ys, zs, ts, tile_u32, dphase, kphase);
+    th::vel_net_tile_h<ACT, true>(*ctl, is, which, outS, xs, ys, zs, ts, 0u, dphase, kphase);
   }
 };
 
