@@ -144,6 +144,8 @@ struct CtlT {
   uint64_t wbar;         // weight-gradient accumulators ready (and their operand tiles free)
   uint64_t abar;         // activation tile of the stash has landed in shared memory
   uint64_t kready[4];    // 32-column group g of the next layer's A operand written (16 warp arrivals)
+  uint64_t dbar2;        // the same pair for the second tile of the two-tile forward evaluation
+  uint64_t kready2[4];
   uint32_t tmem_base;
   uint32_t prog_len;
   const unsigned char* img[NN][NVFI_VEL_LAYERS];  // forward images (W) of the nets
@@ -191,6 +193,8 @@ __device__ inline void setup(CtlT<NN>& c, const NvfiLinear* net0, const NvfiLine
     tc::mbar_init(&c.wbar, 1);
     tc::mbar_init(&c.abar, 1);
     for (int k = 0; k < 4; ++k) tc::mbar_init(&c.kready[k], kThreads / 32);
+    tc::mbar_init(&c.dbar2, 1);
+    for (int k = 0; k < 4; ++k) tc::mbar_init(&c.kready2[k], kThreads / 32);
     tc::fence_barrier_init();
   }
   if (tid < 32) tc::tmem_alloc(&c.tmem_base, tmem_cols);
@@ -274,6 +278,20 @@ __device__ __forceinline__ uint32_t ring_acquire(C& c, Issuer& is) {
   tc::mbar_wait(&c.full[is.c_stage], is.c_round & 1);
   tc::tc_fence_after();
   return is.ring_u32 + is.c_stage * kStageBytes;
+}
+// wait for the K block `ahead` positions after the next one (0 = the next) WITHOUT consuming it; returns
+// its shared-window address.  The blocks are consumed in order with ring_advance.
+template <class C>
+__device__ __forceinline__ uint32_t ring_wait(C& c, Issuer& is, uint32_t ahead) {
+  ring_top_up(c, is, is.in_flight <= ahead);   // block only when that block is not even on its way
+  uint32_t st = is.c_stage + ahead, rd = is.c_round;
+  if (st >= is.n_stages) {
+    st -= is.n_stages;
+    ++rd;
+  }
+  tc::mbar_wait(&c.full[st], rd & 1);
+  tc::tc_fence_after();
+  return is.ring_u32 + st * kStageBytes;
 }
 // after the elected thread has committed empty[c_stage]
 __device__ __forceinline__ void ring_advance(Issuer& is) {
@@ -526,6 +544,158 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
 #pragma unroll
     for (int i = 0; i < 6; ++i)
       outS[i * NVFI_TM + m] = __uint_as_float(raw[i]) + c.bias[which][NVFI_VEL_LAYERS - 1][i];
+  }
+  tc::tc_fence_before();
+  __syncthreads();   // (2)
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Two tiles in flight (the forward kernels).  With one tile the 16 worker warps wait while the last
+// MMAs of a layer drain, and the tensor pipe waits while they run the epilogue.  Here the workers
+// alternate between two tiles of 128 samples: while they run the epilogue of tile 0's layer l, the
+// tensor cores execute tile 1's layer l MMAs (and vice versa), and both tiles consume the SAME weight
+// block from the ring, which halves the weight traffic per sample.  TS form only:
+//   TMEM columns of tile t:  D [256 t, +128)   A_hi [256 t + 128, +64)   A_lo [256 t + 192, +64)
+// D is single-buffered: a warp arrives on kready[t][0] only after it has loaded ALL its accumulator
+// columns, and the issuer starts layer l + 1 of that tile only then.
+// xyzt[t][c][m]: inputs of tile t (c = x, y, z, t), outS[t]: its 6 basis weights [6][128].
+template <int ACT, class C>
+__device__ void vel_net_tile2_h(C& c, Issuer& is_ref, int which, float* const (&outS)[2],
+                                const float* const (&xyzt)[2][4], uint32_t (&dph)[2], uint32_t (&kph)[2]) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == kIssuerWarp) {      // ---- issuer warp
+    Issuer is = is_ref;
+    ring_top_up(c, is, false);
+    __syncthreads();              // (1) both encodings are in tensor memory
+    tc::tc_fence_after();
+    // one 32-column group (2 K steps) of `layer` for tile t against the K block at `stage`
+    auto issue = [&](uint32_t t, int layer, uint32_t g, uint32_t stage, uint64_t* dbar) {
+      const uint32_t n = (layer == NVFI_VEL_LAYERS - 1) ? 16u : 128u;
+      const uint32_t idesc = idesc_f16((int)n);
+      const uint32_t w_hi = desc_lo(stage), w_lo = desc_lo(stage + n * 128u);
+      const uint32_t d = is.tb + 256u * t;
+      if (tc::elect_one()) {
+#pragma unroll
+        for (uint32_t ks = 0; ks < 2; ++ks) {
+          const uint32_t o = ((g & 1u) * 2u + ks) * 2u;
+          const uint32_t ta = d + (2u * g + ks) * 8u;
+          mma_f16_ts(d, ta + 128u, w_hi + o, kDescHiSw128, idesc, (g | ks) ? 1u : 0u);
+          mma_f16_ts(d, ta + 192u, w_hi + o, kDescHiSw128, idesc, 1u);
+          mma_f16_ts(d, ta + 128u, w_lo + o, kDescHiSw128, idesc, 1u);
+        }
+        if (dbar) tc::tc_commit(dbar);
+      }
+      __syncwarp();
+    };
+    auto release = [&]() {        // the MMAs issued so far were the last readers of the oldest block
+      if (tc::elect_one()) tc::tc_commit(&c.empty[is.c_stage]);
+      __syncwarp();
+      ring_advance(is);
+    };
+    {
+      const uint32_t st = ring_wait(c, is, 0);
+      issue(0, 0, 0, st, &c.dbar);
+      issue(1, 0, 0, st, &c.dbar2);
+      release();
+    }
+#pragma unroll 1
+    for (int l = 0; l < NVFI_VEL_LAYERS - 1; ++l) {
+      uint32_t st[2];
+      st[0] = ring_wait(c, is, 0);
+#pragma unroll 1
+      for (uint32_t t = 0; t < 2; ++t) {
+#pragma unroll 1
+        for (uint32_t g = 0; g < 4; ++g) {
+          if (t == 0 && g == 2) st[1] = ring_wait(c, is, 1);
+          else ring_top_up(c, is, false);
+          tc::mbar_wait(t ? &c.kready2[g] : &c.kready[g], kph[t] & 1);
+          tc::tc_fence_after();
+          issue(t, l + 1, g, (g < 2) ? st[0] : st[1], g == 3 ? (t ? &c.dbar2 : &c.dbar) : nullptr);
+          if (t == 1 && (g & 1u)) release();   // g = 1: K block 0, g = 3: K block 1
+        }
+        ++kph[t];
+      }
+    }
+    dph[0] += NVFI_VEL_LAYERS;
+    dph[1] += NVFI_VEL_LAYERS;
+    is_ref = is;
+    __syncthreads();              // (2) outputs complete
+    return;
+  }
+  const int q = warp & 3, h = warp >> 2;
+  const int m = q * 32 + lane;
+  const uint32_t tb = c.tmem_base;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  // ---- PositionEncoder(3) of both tiles (see vel_net_tile_h)
+#pragma unroll 1
+  for (int t = 0; t < 2; ++t) {
+    const float p[4] = {xyzt[t][0][m], xyzt[t][1][m], xyzt[t][2][m], xyzt[t][3][m]};
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float fa = (h <= 1) ? 1.f : ((h == 2) ? 2.f : 4.f), fb = (h == 0) ? 1.f : ((h == 1) ? 2.f : 4.f);
+      float sa, ca, sb, cb;
+      tc::sincos_bounded(p[i] * fa, sa, ca);
+      tc::sincos_bounded(p[i] * fb, sb, cb);
+      v[i] = (h == 0) ? p[i] : ca;
+      v[4 + i] = (h == 3) ? 0.f : sb;
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    tmem_st4(tb + lane_base + 256u * t + 128u + (uint32_t)(4 * h), hi);
+    tmem_st4(tb + lane_base + 256u * t + 192u + (uint32_t)(4 * h), lo);
+  }
+  tc::tmem_st_wait();
+  tc::tc_fence_before();
+  __syncthreads();   // (1)
+
+#pragma unroll 1
+  for (int l = 0; l < NVFI_VEL_LAYERS - 1; ++l) {
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+      tc::mbar_wait(t ? &c.dbar2 : &c.dbar, dph[t] & 1);
+      ++dph[t];
+      tc::tc_fence_after();
+      const uint32_t tcol = tb + lane_base + 256u * (uint32_t)t;
+      uint32_t raw[4][8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tc::tmem_ld8_nowait(tcol + (uint32_t)(h * 8) + 32u * g, raw[g]);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col = g * 32 + h * 8;
+        const float4 b0 = *reinterpret_cast<const float4*>(&c.bias[which][l][col]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&c.bias[which][l][col + 4]);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float av[8], sv;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) av[i] = act_h<ACT>(__uint_as_float(raw[g][i]) + bb[i], sv);
+        uint4 hi, lo;
+        split8(av, hi, lo);
+        tmem_st4(tcol + 128u + (uint32_t)(16 * g + 4 * h), hi);
+        tmem_st4(tcol + 192u + (uint32_t)(16 * g + 4 * h), lo);
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(t ? &c.kready2[g] : &c.kready[g]);
+      }
+      ++kph[t];
+    }
+  }
+  // ---- heads
+#pragma unroll 1
+  for (int t = 0; t < 2; ++t) {
+    tc::mbar_wait(t ? &c.dbar2 : &c.dbar, dph[t] & 1);
+    ++dph[t];
+    tc::tc_fence_after();
+    if (h == 0) {
+      uint32_t raw[8];
+      tc::tmem_ld8_nowait(tb + lane_base + 256u * (uint32_t)t, raw);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+        outS[t][i * NVFI_TM + m] = __uint_as_float(raw[i]) + c.bias[which][NVFI_VEL_LAYERS - 1][i];
+    }
   }
   tc::tc_fence_before();
   __syncthreads();   // (2)

@@ -274,10 +274,185 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
   sample_advect_body<TcMlp>(F, A, B, S, total, n_batches, mode, subs);
 }
 
+// ---------------------------------------------------------------------------------------
+// Product path of the render forward: TWO tiles of 128 samples in flight per CTA (mlp_h.cuh,
+// vel_net_tile2_h): the queue hands out 256 compacted samples at a time; threads 0..255 own one
+// sample each for the per-sample glue (tile = tid >> 7).
+// ---------------------------------------------------------------------------------------
+struct SampleAdvect2Tail {
+  AdvectTile tile[2];
+  int q_idx[2 * NVFI_TM + th::kThreads];
+  float q_x[3][2 * NVFI_TM + th::kThreads];
+  int warp_cnt[2][th::kThreads / 32];
+  int batch;
+};
+
+// integrate_pos on two tiles (advect_tile_with for 256 rows; models/tensorf_keyframe.py:575-611)
+template <class Net2>
+__device__ inline void advect_tile2_with(const NvfiField& F, AdvectTile (&T)[2], Net2 net2) {
+  const int tid = threadIdx.x;
+  const int tt = (tid >> 7) & 1, m = tid & 127;
+  AdvectTile& Tm = T[tt];
+  for (;;) {
+    int active = (tid < 2 * NVFI_TM) ? (fabsf(Tm.off[m]) > 0.f) : 0;
+    if (!__syncthreads_or(active)) break;
+    net2(false);
+    if (tid < 2 * NVFI_TM) {
+      const float off = Tm.off[m];
+      const float a = fabsf(off);
+      float dt = fminf(a, F.dt_max);
+      dt = (off > 0.f) ? dt : ((off < 0.f) ? -dt : 0.f);
+      const float x = Tm.x[0][m], y = Tm.x[1][m], z = Tm.x[2][m];
+      float v[3] = {0.f, 0.f, 0.f};
+      if (!gate_outside(F, x, y, z)) {
+        const float w[6] = {Tm.wout[0][m], Tm.wout[1][m], Tm.wout[2][m], Tm.wout[3][m], Tm.wout[4][m], Tm.wout[5][m]};
+        basis_velocity(w, x, y, z, v);
+      }
+      const float hdt = 0.5f * dt;
+      Tm.xm[0][m] = __fsub_rn(x, __fmul_rn(hdt, v[0]));
+      Tm.xm[1][m] = __fsub_rn(y, __fmul_rn(hdt, v[1]));
+      Tm.xm[2][m] = __fsub_rn(z, __fmul_rn(hdt, v[2]));
+      Tm.tmid[m] = __fsub_rn(Tm.tcur[m], hdt);
+      Tm.dt[m] = dt;
+    }
+    __syncthreads();
+    net2(true);
+    if (tid < 2 * NVFI_TM) {
+      const float off = Tm.off[m];
+      if (fabsf(off) > 0.f) {
+        const float dt = Tm.dt[m];
+        const float xm = Tm.xm[0][m], ym = Tm.xm[1][m], zm = Tm.xm[2][m];
+        float v[3] = {0.f, 0.f, 0.f};
+        if (!gate_outside(F, xm, ym, zm)) {
+          const float w[6] = {Tm.wout[0][m], Tm.wout[1][m], Tm.wout[2][m], Tm.wout[3][m], Tm.wout[4][m], Tm.wout[5][m]};
+          basis_velocity(w, xm, ym, zm, v);
+        }
+        const float x = Tm.x[0][m], y = Tm.x[1][m], z = Tm.x[2][m];
+        float nx = __fsub_rn(x, __fmul_rn(dt, v[0]));
+        float ny = __fsub_rn(y, __fmul_rn(dt, v[1]));
+        float nz = __fsub_rn(z, __fmul_rn(dt, v[2]));
+        if (F.vel_gate == NVFI_GATE_SUR && gate_outside(F, nx, ny, nz)) {  // :603-605
+          nx = x;
+          ny = y;
+          nz = z;
+        }
+        Tm.x[0][m] = nx;
+        Tm.x[1][m] = ny;
+        Tm.x[2][m] = nz;
+        Tm.off[m] = __fsub_rn(off, dt);
+        Tm.tcur[m] = __fsub_rn(Tm.tcur[m], dt);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(th::kLaunchThreads, 1)
     k_sample_advect_h(const __grid_constant__ NvfiField F, const NvfiRenderArgs A,
                       const NvfiRenderBuffers B, int S, long long total, int n_batches, int mode, int subs) {
-  sample_advect_body<HMlp>(F, A, B, S, total, n_batches, mode, subs);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  HMlp mlp;
+  mlp.init(smem_raw, F.vel_net, nullptr, mode);
+  constexpr int NT = HMlp::kThreads;
+  constexpr int TILE2 = 2 * NVFI_TM;
+  SampleAdvect2Tail& sm = *reinterpret_cast<SampleAdvect2Tail*>(smem_raw + HMlp::kBytes);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t dph[2] = {0u, 0u}, kph[2] = {0u, 0u};
+  float* const outS[2] = {&sm.tile[0].wout[0][0], &sm.tile[1].wout[0][0]};
+
+  int sub = subs;
+  long long batch_base = 0;
+  bool exhausted = false;
+  unsigned n_valid = 0;
+  int qc = 0, par = 0;
+  const float off0 = __fsub_rn(A.t, A.base_time);
+
+  for (;;) {
+    // ---- produce: fill the queue up to two tiles
+    while (qc < TILE2 && !exhausted) {
+      if (sub == subs) {
+        if (tid == 0) sm.batch = atomicAdd(&B.counters[0], 1);
+        __syncthreads();
+        const int b = sm.batch;
+        __syncthreads();
+        if (b >= n_batches) {
+          exhausted = true;
+          break;
+        }
+        batch_base = (long long)b * ((long long)subs * NT);
+        sub = 0;
+      }
+      const long long idx = batch_base + (long long)sub * NT + tid;
+      ++sub;
+      bool push = false;
+      float xn[3] = {0.f, 0.f, 0.f};
+      if (tid < NT && idx < total) {
+        push = eval_sample(F, A, B, idx, S, xn);
+        B.valid[idx] = push ? 1 : 0;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, push);
+      if (lane == 0 && warp < NT / 32) sm.warp_cnt[par][warp] = __popc(bal);
+      const int tot = __syncthreads_count(push);
+      if (push) {
+        int pos = qc + __popc(bal & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) pos += sm.warp_cnt[par][w];
+        sm.q_idx[pos] = (int)idx;
+        sm.q_x[0][pos] = xn[0];
+        sm.q_x[1][pos] = xn[1];
+        sm.q_x[2][pos] = xn[2];
+        ++n_valid;
+      }
+      qc += tot;
+      par ^= 1;
+    }
+    if (qc == 0) break;
+    __syncthreads();
+    const int n = min(TILE2, qc);
+    const int start = qc - n;
+    qc = start;
+    // ---- consume two tiles (the second may be partly or wholly padding at the very end)
+    if (tid < TILE2) {
+      AdvectTile& Tm = sm.tile[tid >> 7];
+      const int m = tid & 127;
+      const bool live = tid < n;
+      Tm.x[0][m] = live ? sm.q_x[0][start + tid] : 0.f;
+      Tm.x[1][m] = live ? sm.q_x[1][start + tid] : 0.f;
+      Tm.x[2][m] = live ? sm.q_x[2][start + tid] : 0.f;
+      Tm.tcur[m] = A.t;
+      Tm.off[m] = live ? off0 : 0.f;
+    }
+    __syncthreads();
+    advect_tile2_with(F, sm.tile, [&](bool mid) {
+      AdvectTile& T0 = sm.tile[0];
+      AdvectTile& T1 = sm.tile[1];
+      const float* const in[2][4] = {
+          {mid ? T0.xm[0] : T0.x[0], mid ? T0.xm[1] : T0.x[1], mid ? T0.xm[2] : T0.x[2], mid ? T0.tmid : T0.tcur},
+          {mid ? T1.xm[0] : T1.x[0], mid ? T1.xm[1] : T1.x[1], mid ? T1.xm[2] : T1.x[2], mid ? T1.tmid : T1.tcur}};
+      th::vel_net_tile2_h<ACT_SILU>(*mlp.ctl, mlp.is, 0, outS, in, dph, kph);
+    });
+    if (tid < n) {
+      const AdvectTile& Tm = sm.tile[tid >> 7];
+      const int m = tid & 127;
+      const long long gi = sm.q_idx[start + tid];
+      B.x_adv[gi * 3 + 0] = Tm.x[0][m];
+      B.x_adv[gi * 3 + 1] = Tm.x[1][m];
+      B.x_adv[gi * 3 + 2] = Tm.x[2][m];
+      if (B.x_mid != nullptr) {   // midpoint of the last RK2 step, for the backward pass
+        B.x_mid[gi * 3 + 0] = Tm.xm[0][m];
+        B.x_mid[gi * 3 + 1] = Tm.xm[1][m];
+        B.x_mid[gi * 3 + 2] = Tm.xm[2][m];
+      }
+    }
+    __syncthreads();
+  }
+  mlp.finish();
+  if (B.stats) {
+    float c = warp_sum((float)n_valid);
+    if (lane == 0 && c > 0.f) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(B.stats), (unsigned long long)c);
+      atomicAdd(reinterpret_cast<unsigned long long*>(B.stats) + 1, (unsigned long long)c);
+    }
+  }
 }
 
 // Chunk-global predicate of sample_ray (models/tensorf_base.py:294): one flag per chunk
@@ -507,7 +682,7 @@ extern "C" int nvfi_launch_sample_advect(const NvfiField* F, const NvfiRenderArg
     const int subs = grab_subs(total, HMlp::kThreads, num_sms());
     const int per_batch = subs * HMlp::kThreads;
     const int n_batches = (int)((total + per_batch - 1) / per_batch);
-    const size_t smem = HMlp::kBytes + sizeof(SampleAdvectTail<HMlp::kThreads>);
+    const size_t smem = HMlp::kBytes + sizeof(SampleAdvect2Tail);
     static size_t cached = 0;
     int rc = set_smem(k_sample_advect_h, smem, cached);
     if (rc != NVFI_OK) return rc;
