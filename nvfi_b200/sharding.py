@@ -84,39 +84,101 @@ def gather_frame(parts: Sequence[torch.Tensor], n_rays: int, ray_chunk: int = 20
     return res
 
 
+def shard_index(n_rays: int, rank: int, world_size: int, ray_chunk: int = 2048) -> torch.Tensor:
+    """Ray indices (1-D int64, ascending) of rank ``rank`` under the INTERLEAVED partition: reference
+    chunk c goes to rank c % world_size.  Every reference chunk still lives on exactly one rank (the
+    chunk-global predicate of sample_ray is unchanged), but the ranks' loads are balanced: contiguous
+    blocks of an image give the ranks that own the empty top and bottom rows far less work than the
+    ranks that own the object (strong scaling of one frame)."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank/world_size {rank}/{world_size}")
+    if n_rays < 0 or ray_chunk <= 0:
+        raise ValueError("n_rays must be >= 0 and ray_chunk > 0")
+    n_chunks = (n_rays + ray_chunk - 1) // ray_chunk
+    if rank >= n_chunks:
+        return torch.zeros(0, dtype=torch.int64)
+    chunks = torch.arange(rank, n_chunks, world_size, dtype=torch.int64)
+    idx = (chunks[:, None] * ray_chunk + torch.arange(ray_chunk, dtype=torch.int64)[None, :]).reshape(-1)
+    return idx[idx < n_rays]
+
+
+def gather_frame_interleaved(parts: Sequence[torch.Tensor], n_rays: int, ray_chunk: int = 2048,
+                             group=None) -> List[torch.Tensor]:
+    """Eval with the interleaved partition (``shard_index``): ONE all-gather of the packed per-ray
+    outputs, then each rank's rows are written to their places in the full frame."""
+    rank, ws = world()
+    if ws == 1:
+        return [p for p in parts]
+    widths = [1 if p.dim() == 1 else p.shape[1] for p in parts]
+    n_local = parts[0].shape[0]
+    dev = parts[0].device
+    packed = torch.cat([p.reshape(n_local, -1).float() for p in parts], dim=1).contiguous()
+    index = [shard_index(n_rays, r, ws, ray_chunk) for r in range(ws)]
+    max_n = max(int(i.numel()) for i in index)
+    if n_local < max_n:
+        pad = torch.zeros(max_n - n_local, packed.shape[1], device=dev, dtype=packed.dtype)
+        packed = torch.cat([packed, pad], 0)
+    out = torch.empty(ws * max_n, packed.shape[1], device=dev, dtype=packed.dtype)
+    dist.all_gather_into_tensor(out, packed, group=group)
+    full = torch.empty(n_rays, packed.shape[1], device=dev, dtype=packed.dtype)
+    for r, i in enumerate(index):
+        full[i.to(dev)] = out[r * max_n: r * max_n + i.numel()]
+    res, c = [], 0
+    for p, w in zip(parts, widths):
+        col = full[:, c:c + w]
+        res.append(col.reshape(n_rays) if p.dim() == 1 else col.reshape(n_rays, w))
+        c += w
+    return res
+
+
 def allreduce_grads(params: Iterable[torch.nn.Parameter], extras: Optional[torch.Tensor] = None,
                     group=None, average: bool = False) -> Optional[torch.Tensor]:
-    """Train: ONE all-reduce(sum) over [all param grads || extras] in a flat FP32 buffer.
+    """Train: ONE all-reduce(sum) over [all param grads || has-grad flags || extras] in a flat FP32 buffer.
 
     ``extras`` (1-D tensor) carries scalars that must be summed across ranks as well (loss
-    numerators, ray / point counts); the reduced copy is returned.  Parameters whose grad is
-    None are skipped and stay None, as in the single-process run (the fused backward yields
-    gradients for the same parameter set on every rank whatever its rays hit, so the flat
-    buffers line up).  With ``average`` the
-    gradients are divided by the world size afterwards (use it when every rank's loss is
-    already a mean over its own, equally sized block)."""
+    numerators, ray / point counts); the reduced copy is returned.  The buffer has a slot for EVERY
+    parameter that requires grad, so its length is the same on every rank whatever each rank's rays
+    hit; a parameter whose grad is None contributes zeros and a 0 flag.  After the reduction a
+    parameter receives a gradient iff at least one rank had one (e.g. ``get_vel_loss`` returns python
+    0.0 on a rank with no occupied point and leaves ``a_weight_net`` without grads there, but not on
+    the others); a parameter without a gradient on every rank stays None, as in the single-process
+    run.  With ``average`` the gradients are divided by the world size afterwards (use it when every
+    rank's loss is already a mean over its own, equally sized block)."""
     rank, ws = world()
-    plist = [p for p in params if p.requires_grad and p.grad is not None]
+    plist = [p for p in params if p.requires_grad]
     if ws == 1:
         return extras
+    if not plist and extras is None:
+        return None
     dev = plist[0].device if plist else extras.device
-    numel = sum(p.numel() for p in plist) + (extras.numel() if extras is not None else 0)
+    n_p = len(plist)
+    n_e = extras.numel() if extras is not None else 0
+    numel = sum(p.numel() for p in plist) + n_p + n_e
     flat = torch.zeros(numel, device=dev, dtype=torch.float32)
     off = 0
     for p in plist:
         n = p.numel()
-        flat[off:off + n].copy_(p.grad.reshape(-1))
+        if p.grad is not None:
+            flat[off:off + n].copy_(p.grad.reshape(-1))
         off += n
+    flags_off = off
+    flat[off:off + n_p].copy_(torch.tensor([0.0 if p.grad is None else 1.0 for p in plist], device=dev))
+    off += n_p
     if extras is not None:
         flat[off:].copy_(extras.reshape(-1).float())
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    off = 0
+    has = (flat[flags_off:flags_off + n_p] > 0).tolist()
     scale = 1.0 / ws if average else 1.0
-    for p in plist:
+    off = 0
+    for p, h in zip(plist, has):
         n = p.numel()
-        g = flat[off:off + n].view_as(p)
-        if average:
-            g = g * scale
-        p.grad.copy_(g)
+        if h:
+            g = flat[off:off + n].view_as(p)
+            if average:
+                g = g * scale
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
         off += n
-    return flat[off:].clone() if extras is not None else None
+    return flat[flags_off + n_p:].clone() if extras is not None else None

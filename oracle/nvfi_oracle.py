@@ -441,12 +441,16 @@ def sample_alpha(sc: Scene, xyz: torch.Tensor) -> torch.Tensor:
 def render_chunk(sc: Scene, t: float, o: torch.Tensor, d: torch.Tensor, *, white_bg: bool,
                  training: bool, jitter: Optional[torch.Tensor] = None, random_bg: bool = False,
                  transfer_vel: bool = False, n_samples: Optional[int] = None,
-                 manual_bilerp: bool = False, return_aux: bool = False):
+                 manual_bilerp: bool = False, return_aux: bool = False,
+                 app_mask_override: Optional[torch.Tensor] = None):
     """TensorVMKeyframeTimeKplane.forward + render_pts
     (models/tensorf_keyframe.py:613-755), non-NDC, non-contracted branch.
 
     ``jitter`` (N,1) replaces the CPU-RNG draw at tensorf_base.py:305 (training only);
     ``random_bg`` replaces the ``torch.rand((1,)) < 0.5`` draw at tensorf_keyframe.py:740.
+    ``app_mask_override`` (N,S bool; tests only) replaces the membership test ``weight > thres`` of :719,
+    which is discontinuous: weights within FP32 rounding of the threshold may land on either side, and
+    a gradient comparison has to hold the membership fixed to compare like with like.
     """
     pts, z, valid = sample_ray(sc, o, d, jitter if training else None, n_samples)
     N, S = z.shape
@@ -487,6 +491,8 @@ def render_chunk(sc: Scene, t: float, o: torch.Tensor, d: torch.Tensor, *, white
 
     alpha, weight, _ = raw2alpha(sigma, dists * sc.distance_scale)
     app_mask = weight > sc.ray_march_weight_thres
+    if app_mask_override is not None:
+        app_mask = app_mask_override
     viewdirs = d.view(-1, 1, 3).expand(N, S, 3)
     if app_mask.any():
         af = app_feature(sc, xyzt_eval[app_mask], manual_bilerp)

@@ -68,12 +68,23 @@ def scalar_loss(out, lw):
 
 
 def rel_err(a, b, floor=1.0):
-    """max |a-b| / max(|b|, floor)  — 'relative FP32' with an absolute floor for values near 0."""
+    """max |a-b| / max(|b|, floor)  — element-wise 'relative FP32' with an absolute floor for values near 0
+    (rgb / acc / weights live in [0, 1]: for them this is the largest ABSOLUTE error).  Used together with
+    ``norm_rel_err`` (per-tensor relative L2 norm, no floor) wherever the 1e-4 gate is applied: see
+    ``assert_close``."""
     a = torch.as_tensor(a, dtype=torch.float64)
     b = torch.as_tensor(b, dtype=torch.float64)
     if a.numel() == 0:
         return 0.0
     return float(((a - b).abs() / b.abs().clamp_min(floor)).max())
+
+
+def assert_close(a, b, tol=1e-4, what=""):
+    """The parity gate for value tensors: BOTH the floored element-wise error and the per-tensor relative
+    L2-norm error must be below ``tol``.  Returns (max_abs_floored, rel_norm) for reporting."""
+    e_max, e_norm = rel_err(a, b), norm_rel_err(a, b)
+    assert e_max < tol and e_norm < tol, f"{what}: max |d|/max(|ref|,1) = {e_max:.3e}, ||d||/||ref|| = {e_norm:.3e}"
+    return e_max, e_norm
 
 
 def norm_rel_err(a, b):

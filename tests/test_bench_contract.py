@@ -24,14 +24,17 @@ def _run(args, timeout):
 
 
 def test_reference_arm_line():
-    """`--impl reference`: the oracle port on the host cores, a bounded sample per step, same
-    metric / unit / config as the GPU arm."""
+    """`--impl reference`: the reference's CPU path on the host cores — the unmodified reference from
+    baseline/_ref when installed (kind "reference"), else the oracle port (kind "port") —, a bounded sample
+    per step, same metric / unit / config as the GPU arm."""
     j = _run(["--impl", "reference", "--steps", "1", "--warmup", "0"], timeout=600)
     assert j["impl"] == "reference"
     assert BASE_KEYS <= set(j)
     assert j["unit"] == "rays/s" and j["higher_is_better"] is True and j["vs_baseline"] is None
     assert j["value"] > 0 and j["gpu_launches"] == 0
-    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    installed = os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "models", "nvfi.py"))
+    assert j["cpu_baseline"]["kind"] == ("reference" if installed else "port") and j["cpu_baseline"]["cores"] >= 1
+    assert "stride" in j["cpu_baseline"]["sample"] and "valid-sample fraction" in j["cpu_baseline"]["sample"]
     assert j["cpu_baseline"]["value"] == j["value"] == j["e2e"]["value"]
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in j["config"] and "model" not in j["config"]

@@ -94,3 +94,52 @@ def test_no_grad_mode_and_accumulation(g):
     g1 = p.grad.clone()
     pde.pde_loss_from_points(model.nvfi, xyzt).backward()     # grads accumulate like autograd
     assert norm_rel_err(p.grad, 2 * g1) < 1e-5
+
+
+def test_vel_loss_at_262144_points():
+    """BASELINE.json configs[2] (fallingball, vel_reg_n_pts = 262 144, final 199^3 grid): the loss over all
+    points against (a) the count-weighted mean of the same kernel's losses on 8 disjoint blocks (the
+    residuals of different points are independent: models/nvfi.py:69-84) and (b) the oracle — functorch
+    Jacobian + autograd on the CPU — on a 2 048-point subsample, loss and all 24 gradients."""
+    from nvfi_b200 import pde
+    from nvfi_b200.scenes import build_scene
+    from oracle.scene_io import scene_from_state
+    cfg, nv, sd = build_scene("fallingball", grid=(199, 199, 199))
+    f = nv.nvfi
+    P = int(cfg.experiment.vel_reg_n_pts)
+    assert P == 262144
+    gen = torch.Generator().manual_seed(5)
+    pts = (torch.rand(P, 3, generator=gen) * 2 - 1).cuda()
+    t = torch.rand(P, 1, generator=gen).cuda()
+    keep = pde.occupancy_filter(f, pts, t)
+    n_occ = int(keep.sum())
+    assert 1000 < n_occ < P
+    with torch.no_grad():
+        full = float(nv.get_vel_loss(P, points=pts, t=t))
+        num, den = 0.0, 0
+        for k in range(8):
+            sl = slice(k * P // 8, (k + 1) * P // 8)
+            nk = int(keep[sl].sum())
+            if nk:
+                num += nk * float(nv.get_vel_loss(P // 8, points=pts[sl], t=t[sl]))
+                den += nk
+    assert den == n_occ
+    assert abs(num / den - full) < 1e-5 * max(1.0, abs(full))
+    # oracle on a subsample of the occupied points
+    idx = torch.nonzero(keep).reshape(-1)[torch.randperm(n_occ, generator=gen)[:2048].cuda()]
+    xyzt = torch.cat([pts[idx], t[idx]], -1)
+    sc = scene_from_state(cfg, [199, 199, 199], int(cfg.nvfi.num_keyframes), sd, requires_grad=True)
+    ref = O.pde_loss_from_points(sc, xyzt.cpu())
+    ref.backward()
+    nv.requires_grad_(True)
+    loss = pde.pde_loss_from_points(f, xyzt)
+    assert abs(loss.item() - ref.item()) < TOL * max(1.0, abs(ref.item()))
+    loss.backward()
+    pm = oracle_param_map(sc)
+    params = dict(f.named_parameters())
+    n = 0
+    for name, p in pm.items():
+        if "vel_net" in name and p.grad is not None:
+            assert norm_rel_err(params[name].grad.cpu(), p.grad) < TOL, name
+            n += 1
+    assert n == 24

@@ -51,6 +51,9 @@ def _worker(rank, ws, port, q):
         b, e = sharding.shard_bounds(n, rank, ws, chunk)
         full = sharding.gather_frame([rgb[b:e], depth[b:e]], n, chunk)
         ok_gather = torch.equal(full[0], rgb) and torch.equal(full[1], depth)
+        idx = sharding.shard_index(n, rank, ws, chunk)
+        full2 = sharding.gather_frame_interleaved([rgb[idx], depth[idx]], n, chunk)
+        ok_gather = ok_gather and torch.equal(full2[0], rgb) and torch.equal(full2[1], depth)
 
         # gradient all-reduce: sum over ranks of per-shard gradients == single-process gradient
         w = torch.nn.Parameter(torch.arange(6.0).reshape(2, 3))
@@ -63,6 +66,14 @@ def _worker(rank, ws, port, q):
         ref = ((x @ w_ref.t()) ** 2).sum()
         ref.backward()
         ok_grad = torch.allclose(w.grad, w_ref.grad, rtol=1e-5, atol=1e-5) and unused.grad is None
+        # a parameter that has a gradient on ONE rank only: same buffer length on
+        # every rank, and the gradient arrives everywhere
+        lone = torch.nn.Parameter(torch.zeros(3))
+        if rank == 1:
+            lone.grad = torch.tensor([1.0, 2.0, 3.0])
+        sharding.allreduce_grads([w, lone, unused])
+        ok_grad = ok_grad and lone.grad is not None and torch.equal(lone.grad, torch.tensor([1.0, 2.0, 3.0])) \
+            and unused.grad is None
         ok_extra = abs(float(extras[0]) - float(ref)) < 1e-3 * float(ref) and int(extras[1]) == n
         q.put((rank, ok_gather, ok_grad, ok_extra))
     finally:
@@ -81,6 +92,17 @@ def test_collectives_world_size_2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(r[1] and r[2] and r[3] for r in res), res
+
+
+@pytest.mark.parametrize("n,ws,chunk", [(640000, 8, 2048), (640000, 3, 2048), (100, 4, 7), (5, 8, 1)])
+def test_shard_index_partition(n, ws, chunk):
+    parts = [sharding.shard_index(n, r, ws, chunk) for r in range(ws)]
+    allidx = torch.cat(parts).sort().values
+    assert torch.equal(allidx, torch.arange(n))                   # every ray exactly once
+    for r, p in enumerate(parts):                                 # whole reference chunks, chunk c on rank c % ws
+        assert bool(((p // chunk) % ws == r).all())
+    sizes = [p.numel() for p in parts]
+    assert max(sizes) - min(sizes) <= chunk
 
 
 def test_single_process_passthrough():
