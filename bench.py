@@ -265,6 +265,47 @@ def peaks():
             "source": "fallback (B200_PROFILING.md)"}
 
 
+def measure_live_peaks(dev):
+    """Dense-GEMM and L2 figures measured on this box, right now (extra keys; the roofline `peak` itself
+    stays MEASURED_PEAKS.json's): TF32 / FP16 8192^3 torch.matmul (best of 5) and the bandwidth of a copy
+    between two 24 MB buffers that stay in the 126 MB L2 (read + write bytes)."""
+    out = {}
+    try:
+        n = 8192
+        for name, dt, tf32 in (("tf32_tflops", torch.float32, True), ("fp16_tflops", torch.float16, False)):
+            a = torch.randn(n, n, device=dev, dtype=dt)
+            b = torch.randn(n, n, device=dev, dtype=dt)
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            best = 0.0
+            for i in range(7):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                torch.matmul(a, b)
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 2:
+                    best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+            torch.backends.cuda.matmul.allow_tf32 = prev
+            out[name] = best
+            del a, b
+        x = torch.empty(24 << 20, device=dev, dtype=torch.uint8)
+        y = torch.empty_like(x)
+        for _ in range(5):
+            y.copy_(x)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            y.copy_(x)
+        e1.record()
+        torch.cuda.synchronize()
+        out["l2_copy_gbs"] = 50 * 2 * x.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        out["how"] = "torch.matmul 8192^3 (allow_tf32 / fp16), best of 5; b.copy_(a) on 24 MB buffers x50 (L2-resident)"
+    except Exception as exc:      # never lose the bench line over an extra
+        out["error"] = str(exc)[:200]
+    return out
+
+
 def run_gpu(args):
     import torch.distributed as dist
     from nvfi_b200 import _lib, engine, sharding
@@ -286,52 +327,24 @@ def run_gpu(args):
     assert field.nSamples == 192, field.nSamples
     nv.requires_grad_(True)
     renderer = M.Renderer(nv, 0, 0, RAY_CHUNK)
-    # weak scaling = fixed work per GPU: every rank renders an 800x800 frame of the SAME camera with
-    # its own stratified jitter and target (a different camera per rank changes the number of valid
-    # samples by up to 10 %, and max-over-ranks would then measure the scene, not the system)
-    o_h, d_h = frame_rays(H, W, theta=30.0)
+    # ONE 800x800 frame per step, identical for every world size (same camera, same jitter, same target):
+    # rank r renders the reference chunks c with c % world == r (sharding.shard_index: every 2 048-ray chunk
+    # of models/renderer.py:29-42 lives on exactly one rank, and the empty borders and the object are
+    # spread evenly over the ranks).
+    o_f, d_f = frame_rays(H, W, theta=30.0)
     if args.rows != H:      # profiling aid: a horizontal band through the middle of the frame
         r0 = (H - args.rows) // 2
-        o_h, d_h = o_h[r0 * W:(r0 + args.rows) * W].contiguous(), d_h[r0 * W:(r0 + args.rows) * W].contiguous()
-    n = o_h.shape[0]
-    gen = torch.Generator().manual_seed(1000 + rank)
-    target_h = torch.rand(n, 3, generator=gen)
-    jitter_h = torch.rand(n, 1, generator=gen)
-    o_h, d_h, target_h, jitter_h = (x.pin_memory() for x in (o_h, d_h, target_h, jitter_h))
-    o_d, d_d, target_d, jitter_d = (x.to(dev) for x in (o_h, d_h, target_h, jitter_h))
+        o_f, d_f = o_f[r0 * W:(r0 + args.rows) * W].contiguous(), d_f[r0 * W:(r0 + args.rows) * W].contiguous()
+    n_frame = o_f.shape[0]
+    gen = torch.Generator().manual_seed(1000)
+    target_f = torch.rand(n_frame, 3, generator=gen)
+    jitter_f = torch.rand(n_frame, 1, generator=gen)
     params = [p for p in nv.parameters()]
 
     def barrier():
         if world > 1:
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
-
-    def step_resident(collective=True):
-        """Hot path with inputs resident in HBM."""
-        for p in params:
-            p.grad = None
-        field.train()
-        rgb, depth, acc, w, _ = field.render_rays(T_RENDER, o_d, d_d, white_bg=True, ray_chunk=RAY_CHUNK,
-                                                  jitter=jitter_d)
-        loss = torch.nn.functional.mse_loss(rgb, target_d)
-        loss.backward()
-        if world > 1 and collective:
-            sharding.allreduce_grads(params, average=True)
-        return loss
-
-    def step_e2e():
-        """Public API, host buffers: Ray.to(device) + Renderer.render(mode='train') + MSE + backward
-        + loss.item() (what one iteration of train_nvfi.py does around the render, :156-164, :241-252)."""
-        for p in params:
-            p.grad = None
-        rays = M.Ray(o_h, d_h, cfg.dataset.near, cfg.dataset.far).to(dev, non_blocking=True)
-        tgt = target_h.to(dev, non_blocking=True)
-        rgb, depth, acc, w, _ = renderer.render(T_RENDER, rays, white_background=True, mode="train")
-        loss = torch.nn.functional.mse_loss(rgb, tgt)
-        loss.backward()
-        if world > 1:
-            sharding.allreduce_grads(params, average=True)
-        return float(loss.item()), rays
 
     def timed(fn, k):
         barrier()
@@ -346,35 +359,97 @@ def run_gpu(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    class Job:
+        """The train step on a set of rays of the frame (host-pinned and device-resident copies)."""
+
+        def __init__(self, idx):
+            sel = (lambda x: x) if idx is None else (lambda x: x[idx])
+            self.o_h, self.d_h, self.target_h, self.jitter_h = (
+                sel(x).contiguous().pin_memory() for x in (o_f, d_f, target_f, jitter_f))
+            self.o_d, self.d_d, self.target_d, self.jitter_d = (
+                x.to(dev) for x in (self.o_h, self.d_h, self.target_h, self.jitter_h))
+            self.n = self.o_h.shape[0]
+
+        def loss_of(self, rgb, target):
+            # the frame's MSE: every rank contributes its rays' squared errors over the FRAME's element count,
+            # so the all-reduce(sum) of the gradients gives exactly the single-GPU gradient
+            return ((rgb - target) ** 2).sum() / float(3 * n_frame)
+
+        def resident(self, collective=True):
+            """Hot path with inputs resident in HBM."""
+            for p in params:
+                p.grad = None
+            field.train()
+            rgb, depth, acc, w, _ = field.render_rays(T_RENDER, self.o_d, self.d_d, white_bg=True,
+                                                      ray_chunk=RAY_CHUNK, jitter=self.jitter_d)
+            loss = self.loss_of(rgb, self.target_d)
+            loss.backward()
+            if world > 1 and collective:
+                loss = sharding.allreduce_grads(params, extras=loss.detach().reshape(1))
+            return loss
+
+        def e2e(self):
+            """Public API, host buffers: Ray.to(device) + Renderer.render(mode='train') + MSE + backward
+            + loss.item() (what one iteration of train_nvfi.py does around the render, :156-164, :241-252)."""
+            for p in params:
+                p.grad = None
+            rays = M.Ray(self.o_h, self.d_h, cfg.dataset.near, cfg.dataset.far).to(dev, non_blocking=True)
+            tgt = self.target_h.to(dev, non_blocking=True)
+            rgb, depth, acc, w, _ = renderer.render(T_RENDER, rays, white_background=True, mode="train")
+            loss = self.loss_of(rgb, tgt)
+            loss.backward()
+            if world > 1:
+                loss = sharding.allreduce_grads(params, extras=loss.detach().reshape(1))
+            return float(loss.item()), rays
+
+    # ---- headline: STRONG scaling, one frame per step sharded over the ranks
+    job = Job(sharding.shard_index(n_frame, rank, world, RAY_CHUNK) if world > 1 else None)
     K, Wm = max(1, args.steps), max(3, args.warmup)
     for _ in range(Wm):
-        step_resident()
+        job.resident()
     launches0 = _lib.launch_count()
     clocks = ClockSampler(local_rank) if rank == 0 else None
-    ms_total = timed(step_resident, K)
+    ms_total = timed(job.resident, K)
     clk = clocks.stop() if clocks else None
     launches = (_lib.launch_count() - launches0)
     ms_step = ms_total / K
-    value = world * n / (ms_step * 1e-3)
+    value = n_frame / (ms_step * 1e-3)
 
     # ---- e2e through the public API with host buffers
-    step_e2e()
-    ms_e2e = timed(step_e2e, K) / K
-    _, rays_obj = step_e2e()
-    h2d = sum(b.numel() * b.element_size() for b in rays_obj.buffers()) + target_h.numel() * 4 + n * 4
-    e2e = {"value": world * n / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-           "api": "models.Ray.to(device) + models.Renderer.render(mode='train') + mse + backward + loss.item()"}
+    job.e2e()
+    ms_e2e = timed(job.e2e, K) / K
+    _, rays_obj = job.e2e()
+    h2d = sum(b.numel() * b.element_size() for b in rays_obj.buffers()) + job.target_h.numel() * 4
+    e2e = {"value": n_frame / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": 4 * world,
+           "api": "models.Ray.to(device) + models.Renderer.render(mode='train') + mse + backward + "
+                  "[all-reduce] + loss.item(); bytes are the whole job's (all ranks)"}
+    del rays_obj
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world), "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clk}
 
+    # ---- the step's fixed costs beside the kernels (strong scaling exposes them): the gradient all-reduce
+    if world > 1:
+        ms_ar = timed(lambda: sharding.allreduce_grads(params, extras=torch.zeros(1, device=dev)), K) / K
+        ms_nocoll = timed(lambda: job.resident(collective=False), K) / K
+        line["strong_breakdown"] = {"ms_step": ms_step, "ms_step_without_collective": ms_nocoll,
+                                    "ms_allreduce_alone": ms_ar,
+                                    "rays_per_rank": job.n, "note": "max over ranks, CUDA events"}
+        # ---- weak scaling (round-1 figure): every rank a whole frame, one all-reduce(mean) per step
+        wjob = Job(None)
+        wjob.resident()
+        ms_weak = timed(wjob.resident, max(1, K // 2)) / max(1, K // 2)
+        line["weak"] = {"value": world * n_frame / (ms_weak * 1e-3), "unit": UNIT, "ms_per_step": ms_weak,
+                        "note": "each rank renders its own 800x800 frame (identical work per GPU), gradients all-reduced"}
+        del wjob
+
     # ---- per-kernel device time (CUDA events around every launch, on the launching stream)
     if rank == 0:
-        out = engine.render_forward(field.binding, o_d, d_d, T_RENDER, white_bg=True, training=True,
-                                    jitter=jitter_d, ray_chunk=RAY_CHUNK, want_stats=True)
+        out = engine.render_forward(field.binding, job.o_d, job.d_d, T_RENDER, white_bg=True, training=True,
+                                    jitter=job.jitter_d, ray_chunk=RAY_CHUNK, want_stats=True)
         torch.cuda.synchronize()
         n_valid, n_adv, n_app, _ = (int(x) for x in out.stats.tolist())
         del out
@@ -382,14 +457,16 @@ def run_gpu(args):
         _lib.profile_enable(True)
         P = 2
         for _ in range(P):
-            step_resident(collective=False)     # rank 0 only: no collective in the profiled passes
+            job.resident(collective=False)     # rank 0 only: no collective in the profiled passes
         prof = _lib.profile_read(reset=True)
         _lib.profile_enable(False)
         cnt = engine.LAST_BWD_COUNTERS.view(torch.int64).tolist()
         n_app_bwd, n_adv_bwd = int(cnt[4]), int(cnt[5])
         pk = peaks()
+        live = measure_live_peaks(dev)
+        line["measured_live"] = live
         tf32_peak = 0.5 * pk["bf16_tflops_sustained"]
-        S = 192
+        n, S = job.n, 192
         alg = {   # kernel -> (bound, algorithmic work per launch)
             "k_sample_advect": ("tensor", n_adv * 2 * VEL_EVAL_FLOP),
             "k_sample_advect_tc": ("tensor", n_adv * 2 * VEL_EVAL_FLOP),
@@ -421,19 +498,29 @@ def run_gpu(args):
                 else:
                     ach = work / sec / 1e9
                     e.update(bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"])
+                    if live.get("l2_copy_gbs"):
+                        # the factor planes (<= 37 MB) are L2-resident by design: the meaningful ceiling of a
+                        # gather kernel is the L2, not HBM
+                        e["l2"] = {"achieved": ach, "peak": live["l2_copy_gbs"], "unit": "GB/s",
+                                   "frac": ach / live["l2_copy_gbs"],
+                                   "peak_source": "L2-resident copy measured live (measured_live.l2_copy_gbs)"}
             kern[name] = e
-        # DRAM traffic per launch: per-unit dram__bytes (read + write) of one `ncu --set full` capture
-        # (profiles/ncu_traffic.json, tools/ncu_traffic.py) x the units this run's launch processed
-        traffic = {}
+        # DRAM / L2 traffic per launch: per-unit dram__bytes (read + write) and lts__t_bytes of one
+        # `ncu --set full` capture (profiles/ncu_traffic.json, tools/ncu_traffic.py) x the units this
+        # run's launch processed
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            units = {"valid_samples": n_valid, "advected_samples": n_adv, "advected_samples_bwd": n_adv_bwd}
+            units = {"valid_samples": n_valid, "advected_samples": n_adv, "advected_samples_bwd": n_adv_bwd,
+                     "app_samples": n_app, "app_samples_bwd": n_app_bwd}
             for kname, kv in tj.get("kernels", {}).items():
-                traffic[kname] = kv["dram_bytes_per_unit"] * units[kv["unit"]]
-            for kname, e in kern.items():
-                if kname.split("::")[-1] in traffic:
-                    e["traffic"] = traffic[kname.split("::")[-1]]
+                if kname in kern and kv["unit"] in units:
+                    kern[kname]["traffic"] = kv["dram_bytes_per_unit"] * units[kv["unit"]]
+                    if "lts_bytes_per_unit" in kv:
+                        kern[kname]["l2_traffic"] = kv["lts_bytes_per_unit"] * units[kv["unit"]]
+                    for extra in ("lts_pct_of_peak", "tensor_pipe_pct", "l2_hit_pct"):
+                        if extra in kv:
+                            kern[kname]["ncu_" + extra] = kv[extra]
         top = next(iter(kern))
         r = dict(kern[top])
         line["roofline"] = {"kernel": top, "bound": r.get("bound"), "achieved": r.get("achieved"),
@@ -449,43 +536,153 @@ def run_gpu(args):
                                 ("; TF32 peak = 0.5 x measured sustained bf16" if r.get("bound") == "tensor" else ""))}
         line["roofline_gather"] = dict(kern.get("k_march", {}), kernel="k_march",
                                        note="TensoRF density gather + alpha scan; planes are L2-resident, "
-                                            "so algorithmic GB/s may exceed the HBM copy peak")
+                                            "so algorithmic GB/s may exceed the HBM copy peak: see the 'l2' entry")
         line["kernels"] = kern
         line["counts"] = {"valid_samples": n_valid, "advected_samples": n_adv, "app_samples": n_app,
                           "app_samples_bwd": n_app_bwd, "advected_samples_bwd": n_adv_bwd}
-        # secondary figure (SURVEY.md 8d ii): one 800x800 eval frame, mode='test', no gradients
-        try:
-            field.eval()
+    for p in params:
+        p.grad = None
+
+    # ---- secondary figure (SURVEY.md 8d ii): one 800x800 eval frame, mode='test', sharded + ONE all-gather
+    def eval_leg(fld, t, o_all, d_all, white_bg, transfer, chunk=RAY_CHUNK, reps=3):
+        """Full-frame eval render through the sharded path: each rank renders its interleaved chunks, one
+        all-gather assembles the frame on every rank (sharding.gather_frame_interleaved)."""
+        nfr = o_all.shape[0]
+        idx = sharding.shard_index(nfr, rank, world, chunk) if world > 1 else None
+        o_l = (o_all if idx is None else o_all[idx]).contiguous().to(dev)
+        d_l = (d_all if idx is None else d_all[idx]).contiguous().to(dev)
+        fld.eval()
+
+        def once():
             with torch.no_grad():
-                for _ in range(2):
-                    field.render_rays(T_RENDER, o_d, d_d, white_bg=True, ray_chunk=RAY_CHUNK)
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(3):
-                    field.render_rays(T_RENDER, o_d, d_d, white_bg=True, ray_chunk=RAY_CHUNK)
-                e1.record()
-                torch.cuda.synchronize()
-            ms_eval = e0.elapsed_time(e1) / 3
-            line["eval_frame"] = {"ms": ms_eval, "rays_per_s": n / (ms_eval * 1e-3),
-                                  "note": "render only (mode='test'), rank 0, inputs resident"}
-        except Exception as exc:   # never lose the bench line over the secondary figure
-            line["eval_frame"] = {"error": str(exc)[:200]}
-        finally:
-            field.train()
+                rgb, depth, acc, w, mk = fld.render_rays(t, o_l, d_l, white_bg=white_bg, ray_chunk=chunk,
+                                                        transfer_vel=transfer)
+                parts = [rgb, depth, acc] + ([mk] if fld.mask_field is not None else [])
+                if world > 1:
+                    parts = sharding.gather_frame_interleaved(parts, nfr, chunk)
+            return parts
+        once()
+        ms = timed(once, reps) / reps
+        parts = once()
+        chk = float(parts[0].double().sum().item())
+        return {"ms": ms, "rays_per_s": nfr / (ms * 1e-3), "rays": nfr, "n_gpus": world,
+                "samples_per_ray": int(fld.nSamples), "rgb_checksum": chk}
+
+    try:
+        ev = eval_leg(field, T_RENDER, o_f, d_f, True, False)
+        ev["note"] = "bat, t=0.33, render only (mode='test'), inputs resident, frame sharded + all-gather when n_gpus > 1"
+        line["eval_frame"] = ev
+    except Exception as exc:   # never lose the bench line over a secondary figure
+        line["eval_frame"] = {"error": str(exc)[:200]}
+    field.train()
+
+    if args.rows == H and not args.no_extras:
+        del job
+        line.update(extra_configs(args, dev, rank, world, eval_leg, timed))
+
+    if rank == 0:
         if world == 1 and not args.no_cpu:
             leg = CpuLeg()
             leg.run(0.0, 1)     # warm-up chunk (thread pool, allocator)
             leg.valid = leg.samples = 0
             tt, rr, k = leg.run(args.cpu_budget, 10)
             line["cpu_baseline"] = {"value": rr / tt, "unit": UNIT, "cores": leg.cores, "kind": leg.kind,
-                                    "sample": leg.describe(k, n_valid / float(n * 192))}
+                                    "sample": leg.describe(k, n_valid / float(n_frame * 192))}
         if args.rows != H:
             line["invalid_for_bench"] = f"profiling run on {args.rows} of {H} rows"
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()
+
+
+def extra_configs(args, dev, rank, world, eval_leg, timed):
+    """BASELINE.json configs[2..4] as extra keys of the line (never the headline):
+      pde_262144            fallingball: NVFi.get_vel_loss(262 144) forward + backward (models/nvfi.py:42-84)
+      chessboard_eval_t1.0  chessboard (VelocityAABBSur, K=4, non-white background, the shipped step_ratio):
+                            one 800x800 frame at the extrapolated time t=1.0 (2 RK2 steps), ray-sharded
+      fan_mask_render       fan + MaskField(mask_dim=8) composited in the render, transfer_vel (test_segm_render.py:75-99)
+    """
+    from nvfi_b200 import _lib
+    from nvfi_b200 import models as M
+    from nvfi_b200.scenes import build_scene, frame_rays
+    res = {}
+    torch.cuda.empty_cache()
+    # -- config 3: PDE loss
+    try:
+        cfg, nv, _ = build_scene("fallingball", grid=GRID, device=dev)
+        nv.requires_grad_(True)
+        npts = int(cfg.experiment.vel_reg_n_pts)
+        g = torch.Generator(device=dev).manual_seed(5 + rank)
+        lo, hi = nv.nvfi.aabb
+        pts = nv.nvfi.normalize_coord(torch.rand(npts, 3, device=dev, generator=g) * (hi - lo) + lo)
+        tt = torch.rand(npts, 1, device=dev, generator=g)
+
+        def pde_step():
+            nv.zero_grad(set_to_none=True)
+            loss = nv.get_vel_loss(npts, points=pts, t=tt)
+            if torch.is_tensor(loss):
+                loss.backward()
+            return loss
+        for _ in range(3):
+            pde_step()
+        ms = timed(pde_step, 5) / 5
+        if rank == 0:
+            _lib.profile_read(reset=True)
+            _lib.profile_enable(True)
+            loss = pde_step()
+            torch.cuda.synchronize()
+            prof = _lib.profile_read(reset=True)
+            _lib.profile_enable(False)
+            from nvfi_b200 import pde as _pde
+            with torch.no_grad():
+                kept = int(_pde.occupancy_filter(nv.nvfi, pts, tt).sum())
+            # forward-mode Jacobian: 5 rows per point through weight_net + 1 through a_weight_net, and the
+            # reverse pass of both (x2): algorithmic FLOPs of the loss AND its gradients
+            flop = kept * (5 + 1) * VEL_EVAL_FLOP * 3
+            pk = peaks()
+            res["pde_262144"] = {
+                "ms": ms, "points": npts, "occupied_points": kept, "loss": float(loss),
+                "kernels_ms": {k: v[0] for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:6]},
+                "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12,
+                             "peak": 0.5 * pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                             "frac": flop / (ms * 1e-3) / 1e12 / (0.5 * pk["bf16_tflops_sustained"]),
+                             "note": "whole get_vel_loss call (occupancy filter + Jacobian + reverse pass) against "
+                                     "the TF32 peak (0.5 x sustained bf16); the PDE kernels are FP32 SIMT today"},
+                "note": "fallingball.yaml: get_vel_loss(262144) + backward, per rank (replicated), max over ranks"}
+        del nv
+    except Exception as exc:
+        res["pde_262144"] = {"error": str(exc)[:300]}
+    torch.cuda.empty_cache()
+    # -- config 4: chessboard future-frame extrapolation, ray-sharded eval
+    try:
+        cfg, nv, _ = build_scene("chessboard", grid=GRID, device=dev)
+        o, d = frame_rays(H, W, theta=30.0, phi=-35.0, radius=4.5, z_shift=3.0)
+        r = eval_leg(nv.nvfi, 1.0, o, d, False, False, reps=2)
+        r["note"] = ("chessboard.yaml (VelocityAABBSur, K=4, step_ratio 0.5), 800x800 eval at t=1.0 "
+                     "(extrapolation: 2 RK2 steps), sharded over the ranks + one all-gather")
+        res["chessboard_eval_t1.0"] = r
+        del nv
+    except Exception as exc:
+        res["chessboard_eval_t1.0"] = {"error": str(exc)[:300]}
+    torch.cuda.empty_cache()
+    # -- config 5: fan + mask field
+    try:
+        cfg, nv, _ = build_scene("fan", grid=GRID, device=dev)
+        torch.manual_seed(17)
+        mf = M.MaskField(n_layer=4, n_dim=128, input_dim=3, skips=[], mask_dim=int(cfg.segmentation.n_object),
+                         mask_act="softmax")
+        nv.nvfi.mask_field = mf.to(dev)
+        o, d = frame_rays(H, W, theta=30.0)
+        r = eval_leg(nv.nvfi, 0.5, o, d, True, True, reps=2)
+        r["note"] = ("fan.yaml + MaskField(n_layer=4, n_dim=128, mask_dim=8) composited in the render, "
+                     "mode='test', transfer_vel=True (test_segm_render.py:75-99), sharded + one all-gather")
+        res["fan_mask_render"] = r
+        del nv
+    except Exception as exc:
+        res["fan_mask_render"] = {"error": str(exc)[:300]}
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -495,6 +692,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="nvfi_b200", choices=["nvfi_b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra legs for BASELINE.json configs 3-5")
     ap.add_argument("--rows", type=int, default=H,
                     help="PROFILING ONLY: render the first ROWS rows of the 800x800 frame (ncu replays are "
                          "slow on the 6 GB full-frame working set); the line is marked invalid_for_bench")

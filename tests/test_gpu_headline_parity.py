@@ -111,12 +111,14 @@ def test_eval_outputs_vs_oracle(scene, where, t):
     print(f"[headline parity] {where} t={t}: " + ", ".join(f"{k} max {v[0]:.2e} norm {v[1]:.2e}" for k, v in rep.items()))
 
 
-def _relu_kink_rays(sc, oo, dd, jit, eps=2e-5):
+def _relu_kink_rays(sc, oo, dd, jit, eps=4e-6):
     """Rays with an appearance sample whose MLPRender_PE hidden pre-activation (models/tensorf_base.py:88-98)
     lies within `eps` of zero.  ReLU's derivative jumps there: last-bit differences of the summation order
     decide whether the unit passes its gradient, and ONE such sample moves the first-layer gradients of a
-    2 048-ray chunk by ~3e-3 (measured: tools/diag_app_bisect.py found a pre-activation of -8.7e-7).  Such
-    rays are taken out of the gradient comparison on both sides; their count is reported."""
+    2 048-ray chunk by ~3e-3 (measured: tools/diag_app_bisect.py found a pre-activation of -8.7e-7).  `eps`
+    is the FP32 summation noise of a 110-term dot product of O(1) features (a few 1e-6).  Such rays are
+    taken out of the gradient comparison on both sides; their count is reported and bounded (with 256
+    hidden units and ~3 000 appearance samples per chunk about one ray in a hundred carries such a unit)."""
     from oracle import nvfi_oracle as O
     with torch.no_grad():
         r = O.render_chunk(sc, 0.33, oo, dd, white_bg=True, training=True, jitter=jit, return_aux=True)
@@ -151,7 +153,7 @@ def test_train_gradients_vs_oracle(scene, where):
     target = torch.rand(CHUNK, 3, generator=gen)
     kinks = _relu_kink_rays(make_sc(), oo, dd, jit)
     n_kink = int(kinks.sum())
-    assert n_kink <= 4
+    assert n_kink <= CHUNK // 32, n_kink
     if n_kink:      # same chunk without those rays (the chunk-global inside test does not change: same camera)
         keep = ~kinks
         oo, dd, jit, target = oo[keep].contiguous(), dd[keep].contiguous(), jit[keep].contiguous(), target[keep].contiguous()

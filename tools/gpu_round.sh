@@ -15,7 +15,7 @@ timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6
     python bench.py --steps 1 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_bench.log 2>&1
 # full-set capture of the dominant kernels on a 50-row band of the frame (replays are slow on 6 GB)
 timeout -k 10 900 ncu --set full --clock-control none --import-source on \
-    -k 'regex:^(k_advect_bwd_tc|k_march|k_sample_advect_tc|k_density_bwd)$' --launch-skip 12 -c 4 -f -o $OUT/${TAG}_prof \
+    -k 'regex:^(k_advect_bwd_h|k_march|k_sample_advect_h|k_density_bwd|k_app_bwd|k_appearance)$' --launch-skip 18 -c 6 -f -o $OUT/${TAG}_prof \
     python bench.py --steps 1 --warmup 3 --no-cpu --rows 50 > $OUT/${TAG}_ncu_full.log 2>&1
 ls -la $OUT | tail -8
 fi
