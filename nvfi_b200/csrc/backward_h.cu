@@ -97,6 +97,12 @@ __device__ __forceinline__ float4 ldcg4_now(const float4* p) {
 __device__ __forceinline__ void red_add(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+// The stash of an evaluation is dead once its backward pass has read it: tell the L2 so, or every dirty
+// line is written back to HBM when the next evaluation's stash displaces it (148 CTAs x 608 KB = 90 MB
+// cycle through the cache: ncu showed 9.2 KB of DRAM writes per sample, the whole stash).
+__device__ __forceinline__ void discard_l2(const void* p) {
+  asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
 // Sum over the 32 rows (lanes) of a warp of 8 per-lane values: lane j returns the sum of v[j & 7].
 // Butterfly: 7 exchanges that halve the value count, then 2 plain ones.
 __device__ __forceinline__ float colsum8(const float v[8], int lane) {
@@ -410,6 +416,17 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
     tc::tc_fence_before();   // the D1 reads are ordered before the next barrier (the issuer reuses D1 two layers on)
     NVFI_TLH(160 + L, 0);
   }
+#ifndef NVFI_NO_STASH_DISCARD
+  // every stash line of this evaluation has been consumed (the A tiles through abar -> dW -> wbar, S in
+  // registers): drop them from the L2 without write-back
+  {
+    constexpr int kLinesA = (int)(th::kStashABytes / 128), kLinesS = (int)(th::kStashSFloats * sizeof(float) / 128);
+    for (int i = tid; i < kLinesA; i += NT) discard_l2(stash_a + (size_t)i * 128);
+    const unsigned char* sb = reinterpret_cast<const unsigned char*>(stash_s);
+    for (int i = tid; i < kLinesS; i += NT) discard_l2(sb + (size_t)i * 128);
+    asm volatile("fence.proxy.async.global;" ::: "memory");   // the next evaluation's bulk copies write these lines
+  }
+#endif
 }
 
 // v = basis(w, x): dL/dw and the explicit dL/dx from dL/dv (as in backward.cu)
