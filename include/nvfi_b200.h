@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NVFI_ABI_VERSION 10
+#define NVFI_ABI_VERSION 11
 
 /* error codes */
 #define NVFI_OK 0
@@ -45,12 +45,13 @@ extern "C" {
 #define NVFI_SHADING_MLP_PE 0 /* models/tensorf_base.py:67-98 */
 #define NVFI_SHADING_SH 1     /* models/tensorf_model_utils.py:292-296 */
 
-/* arithmetic of the velocity-MLP GEMMs (nvfi_set_mlp_mode) */
-#define NVFI_MLP_FP32_SIMT 0 /* FP32 FMA tile GEMM (verification path) */
-#define NVFI_MLP_TF32X3 1    /* tcgen05 TF32 tensor cores, 3-term split, activations in tensor memory */
-#define NVFI_MLP_TF32 2      /* tcgen05 single TF32 pass: ~1e-3 relative */
-#define NVFI_MLP_F16X3 3     /* tcgen05 FP16 tensor cores, 2-way operand split (hi + lo, 22 mantissa bits),
-                                3 MMAs per GEMM, operands in shared memory: FP32-grade (default) */
+/* arithmetic of the velocity-MLP GEMMs (NvfiField.mlp_mode; there is no process-wide setting) */
+#define NVFI_MLP_DEFAULT 0   /* = NVFI_MLP_F16X3 */
+#define NVFI_MLP_FP32_SIMT 1 /* FP32 FMA tile GEMM (verification path) */
+#define NVFI_MLP_TF32X3 2    /* tcgen05 TF32 tensor cores, 3-term split, activations in tensor memory */
+#define NVFI_MLP_TF32 3      /* tcgen05 single TF32 pass: ~1e-3 relative */
+#define NVFI_MLP_F16X3 4     /* tcgen05 FP16 tensor cores, 2-way operand split (hi + lo, 22 mantissa bits),
+                                3 MMAs per GEMM: FP32-grade (the product path) */
 
 #define NVFI_GATE_AABB 0 /* VelocityAABB,    models/velocity_field.py:21-33 */
 #define NVFI_GATE_SUR 1  /* VelocityAABBSur, models/velocity_field.py:36-51 */
@@ -129,6 +130,8 @@ typedef struct NvfiField {
   int32_t mask_layers; /* 0 = none; else number of Linear layers incl. the head */
   int32_t mask_dim;
   NvfiLinear mask_net[NVFI_MAX_MASK_LAYERS];
+  /* arithmetic of the velocity-MLP GEMMs for every call that takes this field: NVFI_MLP_* */
+  int32_t mlp_mode;
 } NvfiField;
 
 /* Per-call render arguments: one time for all rays (a render call in the reference
@@ -234,11 +237,6 @@ int nvfi_profile_enable(int on);
 /* Fills up to `cap` entries; returns the number filled (< 0 on error).  reset != 0 clears. */
 int nvfi_profile_read(NvfiProfileEntry* out, int cap, int reset);
 
-/* Selects the arithmetic of the velocity-MLP GEMMs for subsequent calls (process-wide; the
- * default is NVFI_MLP_F16X3, or the value of the environment variable NVFI_MLP_MODE =
- * simt | tf32x3 | tf32 | f16x3 at load).  Returns the previous mode, or NVFI_EINVAL. */
-int nvfi_set_mlp_mode(int mode);
-int nvfi_get_mlp_mode(void);
 
 /* ---- layout packing ----------------------------------------------------------------
  * Replaces nothing in the reference (it reads NCHW through F.grid_sample,
@@ -341,14 +339,6 @@ int nvfi_tv_loss(const float* plane, int C, int H, int W, int time_plane, float 
  * plane and grad must be 16-byte aligned. */
 int nvfi_l1_loss(const float* plane, int64_t n, float offset, float scale, double* loss_accum,
                  float* grad, void* stream);
-
-/* ---- development probe -------------------------------------------------------------------
- * One 128x128x128 TF32 tcgen05 MMA, D[k][n] = sum_m At[k][m] G[m][n], A from tensor memory and
- * B = G read from the sample-major swizzled shared-memory tile of the tensor-core backward
- * with caller-supplied descriptor fields (tests/test_gpu_debug_mma.py pins their meaning). */
-int nvfi_debug_mma_mn(const float* At, const float* G, float* Dout, uint32_t lbo_field,
-                      uint32_t sbo_field, uint32_t kstep_bytes, uint32_t layout_type,
-                      uint32_t b_mn_major, void* stream);
 
 /* Development aid: (tag, clock64) pairs recorded by CTA 0 of the tensor-core backward at its phase
  * boundaries into dev_buf (cap int64 entries); NULL disables. */

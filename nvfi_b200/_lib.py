@@ -12,12 +12,12 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnvfi_b200.so")
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 VEL_LAYERS = 6
 MAX_MASK_LAYERS = 8
 
 ACT_SOFTPLUS, ACT_RELU, ACT_RELU_ABS = 0, 1, 2
-MLP_FP32_SIMT, MLP_TF32X3, MLP_TF32, MLP_F16X3 = 0, 1, 2, 3
+MLP_DEFAULT, MLP_FP32_SIMT, MLP_TF32X3, MLP_TF32, MLP_F16X3 = 0, 1, 2, 3, 4
 SHADING_MLP_PE, SHADING_SH = 0, 1
 GATE_AABB, GATE_SUR = 0, 1
 
@@ -50,6 +50,7 @@ class NvfiField(C.Structure):
         ("alpha_volume", C.c_void_p), ("alpha_grid", I3),
         ("mask_layers", C.c_int32), ("mask_dim", C.c_int32),
         ("mask_net", NvfiLinear * MAX_MASK_LAYERS),
+        ("mlp_mode", C.c_int32),
     ]
 
 
@@ -107,8 +108,6 @@ SIGNATURES = {
     "nvfi_launch_count": (_i64, []),
     "nvfi_profile_enable": (_i, [_i]),
     "nvfi_profile_read": (_i, [C.POINTER(NvfiProfileEntry), _i, _i]),
-    "nvfi_set_mlp_mode": (_i, [_i]),
-    "nvfi_get_mlp_mode": (_i, []),
     "nvfi_pack_linear_umma": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "nvfi_pack_linear_h": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "nvfi_pack_plane": (_i, [_vp, _vp, _i, _i, _i, _vp]),
@@ -129,7 +128,6 @@ SIGNATURES = {
     "nvfi_feature2density": (_i, [C.POINTER(NvfiField), _vp, _i64, _vp, _vp]),
     "nvfi_app_feature": (_i, [C.POINTER(NvfiField), _vp, _i64, _vp, _vp, _vp]),
     "nvfi_velocity": (_i, [C.POINTER(NvfiField), _vp, _i64, _i, _vp, _vp, _vp]),
-    "nvfi_debug_mma_mn": (_i, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
     "nvfi_debug_timeline": (_i, [_vp, _i]),
     "nvfi_tv_loss": (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "nvfi_l1_loss": (_i, [_vp, _i64, _f, _f, _vp, _vp, _vp]),
@@ -157,6 +155,17 @@ def load(path: Optional[str] = None) -> C.CDLL:
         raise RuntimeError(f"nvfi_b200: ABI mismatch (library {v}, binding {ABI_VERSION}); rebuild")
     if path is None:
         _lib = lib
+    return lib
+
+
+def load_debug() -> C.CDLL:
+    """Development probes (include/nvfi_b200_debug.h, csrc/debug/): a separate library, used by tests only."""
+    p = os.path.join(_HERE, "libnvfi_b200_debug.so")
+    if not os.path.exists(p):
+        raise RuntimeError(f"nvfi_b200: {p} not found. Build it with `python -m nvfi_b200.build`.")
+    lib = C.CDLL(p)
+    lib.nvfi_debug_mma_mn.restype = _i
+    lib.nvfi_debug_mma_mn.argtypes = [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp]
     return lib
 
 

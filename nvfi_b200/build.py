@@ -21,6 +21,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 BUILD_DIR = os.path.join(HERE, "csrc", "build")
 LIB_PATH = os.path.join(HERE, "libnvfi_b200.so")
+DEBUG_LIB_PATH = os.path.join(HERE, "libnvfi_b200_debug.so")     # development probes (csrc/debug/), tests only
 
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -40,14 +41,20 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def debug_sources():
+    d = os.path.join(CSRC, "debug")
+    return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(".cu"))
+
+
 def _deps_mtime() -> float:
-    files = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    files = sources() + debug_sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     files += [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
     return max(os.path.getmtime(f) for f in files)
 
 
 def needs_build() -> bool:
-    return not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < _deps_mtime()
+    t = _deps_mtime()
+    return any(not os.path.exists(p) or os.path.getmtime(p) < t for p in (LIB_PATH, DEBUG_LIB_PATH))
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -65,19 +72,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed for {src}:\n{p.stdout}\n{p.stderr}")
         return obj, p.stderr
 
-    with ThreadPoolExecutor(max_workers=min(8, len(sources()))) as ex:
-        results = list(ex.map(compile_one, sources()))
-    objs = [o for o, _ in results]
+    n_prod = len(sources())
+    with ThreadPoolExecutor(max_workers=min(8, n_prod)) as ex:
+        results = list(ex.map(compile_one, sources() + debug_sources()))
+    objs = [o for o, _ in results[:n_prod]]
+    debug_objs = [o for o, _ in results[n_prod:]]
     with open(log_path, "w") as f:
         for _, err in results:
             f.write(err)
     if verbose:
         for _, err in results:
             sys.stderr.write(err)
-    cmd = [nvcc, *ARCH_FLAGS, "-shared", "-o", LIB_PATH, *objs, "-cudart", "static"]
-    p = subprocess.run(cmd, capture_output=True, text=True)
-    if p.returncode != 0:
-        raise RuntimeError(f"link failed:\n{p.stdout}\n{p.stderr}")
+    for out, oo in ((LIB_PATH, objs), (DEBUG_LIB_PATH, debug_objs)):
+        cmd = [nvcc, *ARCH_FLAGS, "-shared", "-o", out, *oo, "-cudart", "static", "-ldl"]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        if p.returncode != 0:
+            raise RuntimeError(f"link failed:\n{p.stdout}\n{p.stderr}")
     return LIB_PATH
 
 

@@ -1,9 +1,6 @@
 // C-ABI entry points (include/nvfi_b200.h): layout packing, ray generation and the
 // forward-render orchestration.  Every function validates its arguments, enqueues
 // kernels on the caller's stream and returns an error code; nothing here touches torch.
-#include <cstdlib>
-#include <cstring>
-
 #include <cuda_fp16.h>
 
 #include "nvfi_common.cuh"
@@ -196,27 +193,6 @@ extern "C" int nvfi_pack_linear_h(const float* w, void* dst, int out_dim, int in
               reinterpret_cast<unsigned char*>(dst), r_valid, c_valid, transposed ? 1 : in_dim,
               transposed ? in_dim : 1, n_rows, k_pad);
   return (int)cudaGetLastError();
-}
-
-static int g_mlp_mode = -1;
-extern "C" int nvfi_get_mlp_mode(void) {
-  if (g_mlp_mode < 0) {
-    g_mlp_mode = NVFI_MLP_F16X3;
-    const char* e = getenv("NVFI_MLP_MODE");
-    if (e) {
-      if (!strcmp(e, "simt")) g_mlp_mode = NVFI_MLP_FP32_SIMT;
-      else if (!strcmp(e, "tf32")) g_mlp_mode = NVFI_MLP_TF32;
-      else if (!strcmp(e, "tf32x3")) g_mlp_mode = NVFI_MLP_TF32X3;
-      else if (!strcmp(e, "f16x3")) g_mlp_mode = NVFI_MLP_F16X3;
-    }
-  }
-  return g_mlp_mode;
-}
-extern "C" int nvfi_set_mlp_mode(int mode) {
-  if (mode < NVFI_MLP_FP32_SIMT || mode > NVFI_MLP_F16X3) return NVFI_EINVAL;
-  const int prev = nvfi_get_mlp_mode();
-  g_mlp_mode = mode;
-  return prev;
 }
 
 extern "C" int nvfi_raygen(const float* pose4x4, int h, int w, float focal,

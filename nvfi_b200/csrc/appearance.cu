@@ -347,15 +347,9 @@ extern "C" int nvfi_launch_appearance(const NvfiField* F, const NvfiRenderArgs* 
   if (rc != NVFI_OK) return rc;
   const int rows = app_act_rows(F);
   const size_t smem = (size_t)rows * NVFI_TM * 4 + 2 * NVFI_KC * 128 * 4 + sizeof(AppTile);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    NVFI_CUDA_OK(cudaFuncSetAttribute(k_appearance, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-    attr_smem = smem;
-  }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  rc = ensure_smem<k_appearance>(smem);
+  if (rc != NVFI_OK) return rc;
+  const int sms = device_sms();
   const int n_batches = (int)((total + NVFI_SUBS * NVFI_THREADS - 1) / (NVFI_SUBS * NVFI_THREADS));
   const int grid = n_batches < sms * 2 ? n_batches : sms * 2;
   NVFI_LAUNCH(k_appearance, grid, NVFI_THREADS, smem, st, *F, *A, *B, S, total, n_batches, rows);
@@ -371,16 +365,10 @@ extern "C" int nvfi_app_feature(const NvfiField* F, const float* xyzt, int64_t n
   cudaStream_t st = (cudaStream_t)stream;
   const int rows = app_act_rows(F);
   const size_t smem = (size_t)rows * NVFI_TM * 4 + 2 * NVFI_KC * 128 * 4 + sizeof(AppTile);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    NVFI_CUDA_OK(cudaFuncSetAttribute(k_app_feature_points,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
+  rc = ensure_smem<k_app_feature_points>(smem);
+  if (rc != NVFI_OK) return rc;
   NVFI_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(int32_t), st));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = device_sms();
   const long long n_tiles = (n + NVFI_TM - 1) / NVFI_TM;
   const int grid = (int)(n_tiles < (long long)sms * 2 ? n_tiles : (long long)sms * 2);
   NVFI_LAUNCH(k_app_feature_points, grid, NVFI_THREADS, smem, st, *F, xyzt, n, feat, counters, rows);

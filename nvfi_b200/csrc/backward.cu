@@ -951,18 +951,12 @@ __global__ void k_reduce_basis(const float* __restrict__ ws, int n_cta, int off,
 
 using namespace nvfi;
 
-extern "C" int nvfi_get_mlp_mode(void);
 extern "C" int nvfi_launch_advect_bwd_tc(const NvfiField*, const NvfiRenderArgs*, const NvfiRenderBuffers*,
                                          const NvfiRenderGrads*, int, long long, int, int, cudaStream_t);
 extern "C" int nvfi_launch_advect_bwd_h(const NvfiField*, const NvfiRenderArgs*, const NvfiRenderBuffers*,
                                         const NvfiRenderGrads*, int, long long, int, cudaStream_t);
 
-static int bwd_num_sms() {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return sms > 0 ? sms : 148;
-}
+static int bwd_num_sms() { return device_sms(); }
 
 extern "C" int64_t nvfi_backward_workspace_bytes(void) {
   return (int64_t)bwd_num_sms() * WS_CTA_F * (int64_t)sizeof(float);
@@ -994,11 +988,9 @@ extern "C" int nvfi_render_backward(const NvfiField* F, const NvfiRenderArgs* A,
     const int s_pad = ((S + 31) / 32) * 32;
     const size_t smem = (size_t)8 * 3 * s_pad * sizeof(double);
     if (smem > 200 * 1024) return NVFI_EUNSUPPORTED;
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-      NVFI_CUDA_OK(cudaFuncSetAttribute(k_march_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-      attr = smem;
+    if (smem > 48 * 1024) {
+      const int rc = ensure_smem<k_march_bwd>(smem);
+      if (rc != NVFI_OK) return rc;
     }
     NVFI_LAUNCH(k_march_bwd, (unsigned)((A->n_rays + 7) / 8), 256, smem, st, *F, *A, *B, *D, S, s_pad);
     NVFI_CUDA_OK(cudaGetLastError());
@@ -1014,11 +1006,9 @@ extern "C" int nvfi_render_backward(const NvfiField* F, const NvfiRenderArgs* A,
     }
     if (!D->g_basis_mat) return NVFI_EINVAL;
     const size_t smem = tile_smem + sizeof(AppBwdTile);
-    static bool attr = false;
-    if (!attr) {
-      NVFI_CUDA_OK(cudaFuncSetAttribute(k_app_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-      attr = true;
+    {
+      const int rc = ensure_smem<k_app_bwd>(smem);
+      if (rc != NVFI_OK) return rc;
     }
     const int grid = n_batches < sms ? n_batches : sms;
     NVFI_LAUNCH(k_app_bwd, grid, NVFI_THREADS, smem, st, *F, *A, *B, *D, S, total, n_batches);
@@ -1052,17 +1042,15 @@ extern "C" int nvfi_render_backward(const NvfiField* F, const NvfiRenderArgs* A,
     for (int l = 0; l < NVFI_VEL_LAYERS; ++l)
       if (!D->g_vel_w[l] || !D->g_vel_b[l] || (l < 5 && !F->vel_net[l].w_rows))
         return NVFI_EINVAL;
-    const int mlp_mode = nvfi_get_mlp_mode();
+    const int mlp_mode = mlp_mode_of(F);
     if (mlp_mode == NVFI_MLP_F16X3)       // product path: FP16-split tcgen05 (backward_h.cu)
       return nvfi_launch_advect_bwd_h(F, A, B, D, S, total, sms, st);
     if (mlp_mode != NVFI_MLP_FP32_SIMT)   // round-1 path: 3xTF32 tcgen05 (backward_tc.cu)
       return nvfi_launch_advect_bwd_tc(F, A, B, D, S, total, sms, mlp_mode, st);
     const size_t smem = tile_smem + sizeof(AdvBwdTile);
-    static bool attr = false;
-    if (!attr) {
-      NVFI_CUDA_OK(cudaFuncSetAttribute(k_advect_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-      attr = true;
+    {
+      const int rc = ensure_smem<k_advect_bwd>(smem);
+      if (rc != NVFI_OK) return rc;
     }
     const int grid = n_batches < sms ? n_batches : sms;
     NVFI_LAUNCH(k_advect_bwd, grid, NVFI_THREADS, smem, st, *F, *A, *B, *D, S, total, n_batches);

@@ -377,6 +377,17 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
     ++wphase;
     tc::tc_fence_after();
     NVFI_TLH(140 + L, 0);
+#ifndef NVFI_NO_STASH_DISCARD
+    // The stash of layer L - 1 is dead: S_{L-1} is in this thread's G_{L-1}, A_{L-1} went through tile tA
+    // into dW(L).  Drop the lines from the L2 now, layer by layer, so that the dirty footprint of the 148
+    // CTAs (which run out of phase) stays near half of 148 x 608 KB.
+    if (L >= 1) {   // 64 KB = 512 lines each: one line per worker thread
+      discard_l2(reinterpret_cast<const unsigned char*>(stash_s) + (size_t)(L - 1) * 65536 + (size_t)tid * 128);
+      if (L <= 4) discard_l2(stash_a + 32768 + (size_t)(L - 1) * th::kTileBytes + (size_t)tid * 128);
+    } else if (tid < 256) {
+      discard_l2(stash_a + (size_t)tid * 128);   // the encoding (hi | lo slab 0)
+    }
+#endif
     if (L > 0) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -416,17 +427,7 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
     tc::tc_fence_before();   // the D1 reads are ordered before the next barrier (the issuer reuses D1 two layers on)
     NVFI_TLH(160 + L, 0);
   }
-#ifndef NVFI_NO_STASH_DISCARD
-  // every stash line of this evaluation has been consumed (the A tiles through abar -> dW -> wbar, S in
-  // registers): drop them from the L2 without write-back
-  {
-    constexpr int kLinesA = (int)(th::kStashABytes / 128), kLinesS = (int)(th::kStashSFloats * sizeof(float) / 128);
-    for (int i = tid; i < kLinesA; i += NT) discard_l2(stash_a + (size_t)i * 128);
-    const unsigned char* sb = reinterpret_cast<const unsigned char*>(stash_s);
-    for (int i = tid; i < kLinesS; i += NT) discard_l2(sb + (size_t)i * 128);
-    asm volatile("fence.proxy.async.global;" ::: "memory");   // the next evaluation's bulk copies write these lines
-  }
-#endif
+  asm volatile("fence.proxy.async.global;" ::: "memory");   // the next evaluation's bulk copies rewrite the discarded lines
 }
 
 // v = basis(w, x): dL/dw and the explicit dL/dx from dL/dv (as in backward.cu)
@@ -754,10 +755,9 @@ extern "C" int nvfi_launch_advect_bwd_h(const NvfiField* F, const NvfiRenderArgs
   if (F->vel_net[5].n_pad != 8) return NVFI_EUNSUPPORTED;
   const size_t smem = 1024 + 2 * (size_t)th::kTileBytes + (size_t)thb::kStages * th::kStageBytes +
                       ((sizeof(th::Ctl1) + 127) & ~(size_t)127) + sizeof(thb::BwdTile);
-  static size_t cached = 0;
-  if (smem > cached) {
-    NVFI_CUDA_OK(cudaFuncSetAttribute(thb::k_advect_bwd_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cached = smem;
+  {
+    const int rc = ensure_smem<thb::k_advect_bwd_h>(smem);
+    if (rc != NVFI_OK) return rc;
   }
   const int subs = grab_subs(total, thb::NT, sms);
   const int per_batch = subs * thb::NT;

@@ -827,13 +827,13 @@ __global__ void __launch_bounds__(tc::kLaunchThreads, 1)
 
 using namespace nvfi;
 
-extern "C" int nvfi_get_mlp_mode(void);
 static_assert(tcb::TW_TOTAL <= WS_CTA_F, "per-CTA workspace of the tensor-core backward exceeds WS_CTA_F");
 
 extern "C" int nvfi_debug_timeline_h(long long* dev_buf, int cap);
 extern "C" int nvfi_debug_timeline(long long* dev_buf, int cap) {
   const int zero = 0;
-  if (nvfi_get_mlp_mode() == NVFI_MLP_F16X3) return nvfi_debug_timeline_h(dev_buf, cap);
+  const int rc = nvfi_debug_timeline_h(dev_buf, cap);   // both tensor-core backward kernels get the buffer
+  if (rc != NVFI_OK) return rc;
   NVFI_CUDA_OK(cudaMemcpyToSymbol(tcb::g_tl_buf, &dev_buf, sizeof(dev_buf)));
   NVFI_CUDA_OK(cudaMemcpyToSymbol(tcb::g_tl_cap, &cap, sizeof(cap)));
   NVFI_CUDA_OK(cudaMemcpyToSymbol(tcb::g_tl_n, &zero, sizeof(zero)));
@@ -851,11 +851,9 @@ extern "C" int nvfi_launch_advect_bwd_tc(const NvfiField* F, const NvfiRenderArg
   if (F->vel_net[5].n_pad != 8) return NVFI_EUNSUPPORTED;
   const size_t smem = 1024 + (size_t)tcb::kBwdStages * tc::kStageBytes + 2 * 65536 + sizeof(tc::Ctl) +
                       sizeof(tcb::BwdTile);
-  static size_t cached = 0;
-  if (smem > cached) {
-    NVFI_CUDA_OK(cudaFuncSetAttribute(tcb::k_advect_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-    cached = smem;
+  {
+    const int rc = ensure_smem<tcb::k_advect_bwd_tc>(smem);
+    if (rc != NVFI_OK) return rc;
   }
   const int subs = grab_subs(total, tcb::NT, sms);
   const int per_batch = subs * tcb::NT;

@@ -3,6 +3,7 @@
 // sample-major swizzled shared-memory tile used by the tensor-core backward, with the
 // descriptor fields supplied by the caller.  tests/test_gpu_debug_mma.py pins the field
 // semantics the backward relies on against a host GEMM.
+#include "nvfi_b200_debug.h"
 #include "mlp_tc.cuh"
 
 namespace nvfi {
@@ -88,13 +89,8 @@ extern "C" int nvfi_debug_mma_mn(const float* At, const float* G, float* Dout, u
                                  uint32_t b_mn_major, void* stream) {
   if (!At || !G || !Dout) return NVFI_EINVAL;
   const size_t smem = 65536 + 1024;
-  static bool attr = false;
-  if (!attr) {
-    NVFI_CUDA_OK(cudaFuncSetAttribute(nvfi::k_debug_mma_mn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-    attr = true;
-  }
-  NVFI_LAUNCH(nvfi::k_debug_mma_mn, 1, 128, smem, (cudaStream_t)stream, At, G, Dout, lbo_field, sbo_field,
-              kstep_bytes, layout_type, b_mn_major);
+  NVFI_CUDA_OK(cudaFuncSetAttribute(nvfi::k_debug_mma_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nvfi::k_debug_mma_mn<<<1, 128, smem, (cudaStream_t)stream>>>(At, G, Dout, lbo_field, sbo_field, kstep_bytes,
+                                                               layout_type, b_mn_major);
   return (int)cudaGetLastError();
 }

@@ -195,11 +195,9 @@ extern "C" int nvfi_launch_march(const NvfiField* F, const NvfiRenderArgs* A,
   const int s_pad = ((S + 31) / 32) * 32;
   const size_t smem = (size_t)MARCH_WARPS * s_pad * sizeof(float);
   if (smem > 200 * 1024) return NVFI_EUNSUPPORTED;
-  static size_t attr_smem = 0;
-  if (smem > 48 * 1024 && smem > attr_smem) {
-    NVFI_CUDA_OK(
-        cudaFuncSetAttribute(k_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+  if (smem > 48 * 1024) {
+    const int rc = ensure_smem<k_march>(smem);
+    if (rc != NVFI_OK) return rc;
   }
   const long long grid = (A->n_rays + MARCH_WARPS - 1) / MARCH_WARPS;
   NVFI_LAUNCH(k_march, (unsigned)grid, MARCH_WARPS * 32, smem, st, *F, *A, *B, S, s_pad);

@@ -41,6 +41,44 @@
 
 namespace nvfi {
 
+// Arithmetic of the velocity-MLP GEMMs of a call (NvfiField.mlp_mode; 0 / out of range = the product path).
+inline int mlp_mode_of(const NvfiField* F) {
+  const int m = F->mlp_mode;
+  return (m < NVFI_MLP_FP32_SIMT || m > NVFI_MLP_F16X3) ? NVFI_MLP_F16X3 : m;
+}
+
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = kMaxDevices - 1;
+  return dev;
+}
+// Opt-in to more than 48 KB of dynamic shared memory.  cudaFuncSetAttribute is per DEVICE, so the
+// "already done" cache is per (kernel, device): one instantiation of this template per kernel.
+template <auto Kernel>
+inline int ensure_smem(size_t smem) {
+  static size_t cached[kMaxDevices] = {};
+  const int dev = current_device();
+  if (smem > cached[dev] || dev == kMaxDevices - 1) {
+    const cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cached[dev] = smem;
+  }
+  return 0;
+}
+// SM count of the current device (per-device cache).
+inline int device_sms() {
+  static int cached[kMaxDevices] = {};
+  const int dev = current_device();
+  if (cached[dev] <= 0) {
+    int n = 0, d = 0;
+    cudaGetDevice(&d);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
+    cached[dev] = n > 0 ? n : 148;
+  }
+  return cached[dev];
+}
+
 // Sub-batches (of `threads` raw samples) per atomically grabbed batch of the persistent
 // compaction kernels: NVFI_SUBS when there is plenty of work, fewer when the launch would
 // otherwise have fewer than ~6 batches per SM.

@@ -428,12 +428,7 @@ __global__ void __launch_bounds__(NVFI_THREADS, 1)
 
 using namespace nvfi;
 
-static int pde_sms() {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return sms > 0 ? sms : 148;
-}
+static int pde_sms() { return device_sms(); }
 
 static void reduce_net(const float* ws, int grid, float* const gw[NVFI_VEL_LAYERS],
                        float* const gb[NVFI_VEL_LAYERS], cudaStream_t st) {
@@ -476,11 +471,9 @@ extern "C" int nvfi_pde_loss(const NvfiField* F, const float* xyzt, const float*
   const size_t tile_smem = (size_t)(2 * TILE_F + 2 * NVFI_KC * 128) * sizeof(float);
   {
     const size_t smem = tile_smem + sizeof(PdeTile);
-    static bool attr = false;
-    if (!attr) {
-      NVFI_CUDA_OK(cudaFuncSetAttribute(k_pde_jac, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-      attr = true;
+    {
+      const int rc = ensure_smem<k_pde_jac>(smem);
+      if (rc != NVFI_OK) return rc;
     }
     const long long n_tiles = (n + PDE_PTS - 1) / PDE_PTS;
     const int grid = (int)(n_tiles < sms ? n_tiles : sms);
@@ -491,11 +484,9 @@ extern "C" int nvfi_pde_loss(const NvfiField* F, const float* xyzt, const float*
   }
   if (want_grad) {
     const size_t smem = tile_smem + sizeof(AccBwdTile);
-    static bool attr = false;
-    if (!attr) {
-      NVFI_CUDA_OK(cudaFuncSetAttribute(k_accnet_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-      attr = true;
+    {
+      const int rc = ensure_smem<k_accnet_bwd>(smem);
+      if (rc != NVFI_OK) return rc;
     }
     const long long n_tiles = (n + NVFI_TM - 1) / NVFI_TM;
     const int grid = (int)(n_tiles < sms ? n_tiles : sms);

@@ -2,10 +2,14 @@
 // "instrumentation").  Every kernel launch of the library goes through a ProfScope: it
 // always counts the launch (bench.py reports `gpu_launches` from this counter) and, when
 // profiling is enabled, brackets the launch with two CUDA events on the launching stream so
-// that bench.py can attribute device time to kernels without running under a profiler.
+// that bench.py can attribute device time to kernels without running under a profiler.  It also
+// opens an NVTX range named after the kernel around the launch (header-only NVTX3: a no-op unless a
+// tool such as nsys / ncu --nvtx is attached).
 #include <mutex>
 #include <string>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "nvfi_common.cuh"
 
@@ -36,6 +40,7 @@ static cudaEvent_t get_event() {
 ProfScope::ProfScope(const char* name, cudaStream_t st) : st_(st), idx_(-1) {
   for (const char* p = name; *p; ++p)   // drop namespace qualifiers: "tcb::k_x" -> "k_x"
     if (p[0] == ':' && p[1] == ':') name = p + 2;
+  nvtxRangePushA(name);
   std::lock_guard<std::mutex> lk(g_mu);
   ++g_launches;
   if (!g_enabled) return;
@@ -46,9 +51,11 @@ ProfScope::ProfScope(const char* name, cudaStream_t st) : st_(st), idx_(-1) {
 }
 
 ProfScope::~ProfScope() {
-  if (idx_ < 0) return;
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (idx_ < (int)g_records.size()) cudaEventRecord(g_records[idx_].e1, st_);
+  if (idx_ >= 0) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (idx_ < (int)g_records.size()) cudaEventRecord(g_records[idx_].e1, st_);
+  }
+  nvtxRangePop();
 }
 
 }  // namespace nvfi

@@ -626,18 +626,7 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
 
 using namespace nvfi;
 
-static int g_num_sms = 0;
-static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
-
-extern "C" int nvfi_get_mlp_mode(void);
+static int num_sms() { return device_sms(); }
 
 // The tensor-core path needs the weight images of every layer.
 static bool has_umma(const NvfiLinear* net) {
@@ -650,15 +639,6 @@ static bool has_himg(const NvfiLinear* net) {
   for (int l = 0; l < NVFI_VEL_LAYERS; ++l)
     if (!net[l].himg) return false;
   return true;
-}
-
-template <class K>
-static int set_smem(K kernel, size_t smem, size_t& cached) {
-  if (smem > cached) {
-    NVFI_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cached = smem;
-  }
-  return NVFI_OK;
 }
 
 extern "C" int nvfi_launch_sample_advect(const NvfiField* F, const NvfiRenderArgs* A,
@@ -676,15 +656,14 @@ extern "C" int nvfi_launch_sample_advect(const NvfiField* F, const NvfiRenderArg
     NVFI_LAUNCH(k_sample_only, grid, 256, 0, st, *F, *A, *B, S, total);
     return (int)cudaGetLastError();
   }
-  const int mode = nvfi_get_mlp_mode();
+  const int mode = mlp_mode_of(F);
   if (mode == NVFI_MLP_F16X3) {
     if (!has_himg(F->vel_net)) return NVFI_EINVAL;
     const int subs = grab_subs(total, HMlp::kThreads, num_sms());
     const int per_batch = subs * HMlp::kThreads;
     const int n_batches = (int)((total + per_batch - 1) / per_batch);
     const size_t smem = HMlp::kBytes + sizeof(SampleAdvect2Tail);
-    static size_t cached = 0;
-    int rc = set_smem(k_sample_advect_h, smem, cached);
+    int rc = ensure_smem<k_sample_advect_h>(smem);
     if (rc != NVFI_OK) return rc;
     const int grid = min(n_batches, num_sms());
     NVFI_LAUNCH(k_sample_advect_h, grid, HMlp::kLaunchThreads, smem, st, *F, *A, *B, S, total, n_batches, mode, subs);
@@ -698,8 +677,7 @@ extern "C" int nvfi_launch_sample_advect(const NvfiField* F, const NvfiRenderArg
     const int per_batch = subs * TcMlp::kThreads;
     const int n_batches = (int)((total + per_batch - 1) / per_batch);
     const size_t smem = TcMlp::kBytes + sizeof(SampleAdvectTail<TcMlp::kThreads>);
-    static size_t cached = 0;
-    int rc = set_smem(k_sample_advect_tc, smem, cached);
+    int rc = ensure_smem<k_sample_advect_tc>(smem);
     if (rc != NVFI_OK) return rc;
     const int grid = min(n_batches, num_sms());
     NVFI_LAUNCH(k_sample_advect_tc, grid, TcMlp::kLaunchThreads, smem, st, *F, *A, *B, S, total, n_batches, mode, subs);
@@ -707,8 +685,7 @@ extern "C" int nvfi_launch_sample_advect(const NvfiField* F, const NvfiRenderArg
   }
   const int n_batches = (int)((total + NVFI_SUBS * NVFI_THREADS - 1) / (NVFI_SUBS * NVFI_THREADS));
   const size_t smem = SimtMlp::kBytes + sizeof(SampleAdvectTail<NVFI_THREADS>);
-  static size_t cached = 0;
-  int rc = set_smem(k_sample_advect, smem, cached);
+  int rc = ensure_smem<k_sample_advect>(smem);
   if (rc != NVFI_OK) return rc;
   const int grid = min(n_batches, num_sms() * 2);
   NVFI_LAUNCH(k_sample_advect, grid, NVFI_THREADS, smem, st, *F, *A, *B, S, total, n_batches);
@@ -723,12 +700,11 @@ extern "C" int nvfi_integrate_pos(const NvfiField* F, const float* x, const floa
   cudaStream_t st = (cudaStream_t)stream;
   NVFI_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(int32_t), st));
   const long long n_tiles = (n + NVFI_TM - 1) / NVFI_TM;
-  const int mode = nvfi_get_mlp_mode();
+  const int mode = mlp_mode_of(F);
   if (mode == NVFI_MLP_F16X3) {
     if (!has_himg(F->vel_net)) return NVFI_EINVAL;
     const size_t smem = HMlp::kBytes + sizeof(PointAdvectTail);
-    static size_t cached = 0;
-    int rc = set_smem(k_integrate_pos_h, smem, cached);
+    int rc = ensure_smem<k_integrate_pos_h>(smem);
     if (rc != NVFI_OK) return rc;
     const int grid = (int)(n_tiles < (long long)num_sms() ? n_tiles : (long long)num_sms());
     NVFI_LAUNCH(k_integrate_pos_h, grid, HMlp::kLaunchThreads, smem, st, *F, x, t, base, n, out, counters, mode);
@@ -737,16 +713,14 @@ extern "C" int nvfi_integrate_pos(const NvfiField* F, const float* x, const floa
   if (mode != NVFI_MLP_FP32_SIMT) {
     if (!has_umma(F->vel_net)) return NVFI_EINVAL;
     const size_t smem = TcMlp::kBytes + sizeof(PointAdvectTail);
-    static size_t cached = 0;
-    int rc = set_smem(k_integrate_pos_tc, smem, cached);
+    int rc = ensure_smem<k_integrate_pos_tc>(smem);
     if (rc != NVFI_OK) return rc;
     const int grid = (int)(n_tiles < (long long)num_sms() ? n_tiles : (long long)num_sms());
     NVFI_LAUNCH(k_integrate_pos_tc, grid, TcMlp::kLaunchThreads, smem, st, *F, x, t, base, n, out, counters, mode);
     return (int)cudaGetLastError();
   }
   const size_t smem = SimtMlp::kBytes + sizeof(PointAdvectTail);
-  static size_t cached = 0;
-  int rc = set_smem(k_integrate_pos, smem, cached);
+  int rc = ensure_smem<k_integrate_pos>(smem);
   if (rc != NVFI_OK) return rc;
   const int grid = (int)(n_tiles < (long long)num_sms() * 2 ? n_tiles : (long long)num_sms() * 2);
   NVFI_LAUNCH(k_integrate_pos, grid, NVFI_THREADS, smem, st, *F, x, t, base, n, out, counters);
@@ -760,12 +734,11 @@ extern "C" int nvfi_velocity(const NvfiField* F, const float* xyzt, int64_t n, i
   cudaStream_t st = (cudaStream_t)stream;
   NVFI_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(int32_t), st));
   const long long n_tiles = (n + NVFI_TM - 1) / NVFI_TM;
-  const int mode = nvfi_get_mlp_mode();
+  const int mode = mlp_mode_of(F);
   if (mode == NVFI_MLP_F16X3) {
     if (!has_himg(F->vel_net) || (full && !has_himg(F->acc_net))) return NVFI_EINVAL;
     const size_t smem = HMlp::kBytes + sizeof(PointAdvectTail);
-    static size_t cached = 0;
-    int rc = set_smem(k_velocity_h, smem, cached);
+    int rc = ensure_smem<k_velocity_h>(smem);
     if (rc != NVFI_OK) return rc;
     const int grid = (int)(n_tiles < (long long)num_sms() ? n_tiles : (long long)num_sms());
     NVFI_LAUNCH(k_velocity_h, grid, HMlp::kLaunchThreads, smem, st, *F, xyzt, n, full, out, counters, mode);
@@ -774,16 +747,14 @@ extern "C" int nvfi_velocity(const NvfiField* F, const float* xyzt, int64_t n, i
   if (mode != NVFI_MLP_FP32_SIMT) {
     if (!has_umma(F->vel_net) || (full && !has_umma(F->acc_net))) return NVFI_EINVAL;
     const size_t smem = TcMlp::kBytes + sizeof(PointAdvectTail);
-    static size_t cached = 0;
-    int rc = set_smem(k_velocity_tc, smem, cached);
+    int rc = ensure_smem<k_velocity_tc>(smem);
     if (rc != NVFI_OK) return rc;
     const int grid = (int)(n_tiles < (long long)num_sms() ? n_tiles : (long long)num_sms());
     NVFI_LAUNCH(k_velocity_tc, grid, TcMlp::kLaunchThreads, smem, st, *F, xyzt, n, full, out, counters, mode);
     return (int)cudaGetLastError();
   }
   const size_t smem = SimtMlp::kBytes + sizeof(PointAdvectTail);
-  static size_t cached = 0;
-  int rc = set_smem(k_velocity, smem, cached);
+  int rc = ensure_smem<k_velocity>(smem);
   if (rc != NVFI_OK) return rc;
   const int grid = (int)(n_tiles < (long long)num_sms() * 2 ? n_tiles : (long long)num_sms() * 2);
   NVFI_LAUNCH(k_velocity, grid, NVFI_THREADS, smem, st, *F, xyzt, n, full, out, counters);

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -29,14 +30,28 @@ MAT_MODE_TIME = ((2, 3), (1, 3), (0, 3))
 MLP_MODES = {"simt": L.MLP_FP32_SIMT, "tf32x3": L.MLP_TF32X3, "tf32": L.MLP_TF32, "f16x3": L.MLP_F16X3}
 
 
+_mlp_mode = os.environ.get("NVFI_MLP_MODE", "f16x3")
+if _mlp_mode not in MLP_MODES:
+    raise RuntimeError(f"nvfi_b200: NVFI_MLP_MODE={_mlp_mode!r} (expected one of {sorted(MLP_MODES)})")
+
+
 def set_mlp_mode(mode: str) -> str:
     """Arithmetic of the velocity-MLP GEMMs: 'f16x3' (tcgen05 FP16 tensor cores, 2-way operand split,
     FP32-grade; default), 'tf32x3' (round-1 path: 3-term TF32 split, activations in tensor memory),
-    'tf32' (single TF32 pass) or 'simt' (FP32 FMA verification path).  Returns the previous mode."""
-    prev = L.load().nvfi_set_mlp_mode(MLP_MODES[mode])
-    if prev < 0:
-        raise RuntimeError("nvfi_b200: bad mlp mode")
-    return {v: k for k, v in MLP_MODES.items()}[prev]
+    'tf32' (single TF32 pass) or 'simt' (FP32 FMA verification path).  Returns the previous mode.
+
+    The library itself has no process-wide state: the mode travels with every call in
+    ``NvfiField.mlp_mode`` (include/nvfi_b200.h).  This host-side default is what ``FieldBinding.sync``
+    writes there unless the binding carries its own ``mlp_mode``."""
+    global _mlp_mode
+    if mode not in MLP_MODES:
+        raise RuntimeError(f"nvfi_b200: bad mlp mode {mode!r}")
+    prev, _mlp_mode = _mlp_mode, mode
+    return prev
+
+
+def get_mlp_mode() -> str:
+    return _mlp_mode
 
 
 def _stream() -> int:
@@ -56,16 +71,25 @@ def _f32(x) -> float:
     return float(torch.tensor(float(x), dtype=torch.float32))
 
 
+_EPOCH = 0          # bumped by FieldBinding.invalidate(): part of every cache key
+_STRICT_SYNC = os.environ.get("NVFI_STRICT_SYNC", "0") not in ("", "0")   # debug aid: re-pack on every call
+
+
 class _Tracked:
-    """Remembers (data_ptr, version) of source tensors to know when a packed copy is stale."""
+    """Remembers (data_ptr, version, shape) of source tensors to know when a packed copy is stale.
+
+    Every in-place operation on a parameter bumps its ``_version`` (optimizer steps, ``copy_`` under
+    ``no_grad``, ``load_state_dict``).  Writes through ``p.data`` do NOT (``p.data.clamp_()`` leaves
+    ``p._version`` unchanged): after such a write call ``FieldBinding.invalidate()`` (or
+    ``field.invalidate_packed()``), or run with NVFI_STRICT_SYNC=1, which re-packs on every call."""
 
     def __init__(self):
         self.key = None
 
     def stale(self, tensors: Sequence[Optional[torch.Tensor]]) -> bool:
-        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) if t is not None else None
-                    for t in tensors)
-        if key != self.key:
+        key = (_EPOCH,) + tuple((t.data_ptr(), t._version, tuple(t.shape)) if t is not None else None
+                                for t in tensors)
+        if key != self.key or _STRICT_SYNC:
             self.key = key
             return True
         return False
@@ -208,8 +232,20 @@ class FieldBinding:
         self.mask_key = None
         self.alpha_track = _Tracked()
         self.alpha_u8: Optional[torch.Tensor] = None
+        self.mlp_mode: Optional[str] = None      # None = the host-side default (set_mlp_mode)
+        self.scalar_track = _Tracked()
+        self.scalars = None
 
     # -- helpers --------------------------------------------------------------------------
+    @staticmethod
+    def invalidate():
+        """Forget every packed copy (planes, MLP weights and their tensor-core images, the alpha volume):
+        the next call re-packs from the parameters.  Needed only after writes that bypass autograd's
+        version counter (``p.data.<op>_()``); the model calls it from ``upsample_volume_grid``,
+        ``shrink``, ``updateAlphaMask`` and ``load_state_dict``."""
+        global _EPOCH
+        _EPOCH += 1
+
     def _device(self):
         return self.field.density_plane_space[0].device
 
@@ -219,21 +255,33 @@ class FieldBinding:
         dev = self._device()
         if dev.type != "cuda":
             raise RuntimeError("nvfi_b200: the field must live on a CUDA device (no CPU fallback)")
-        aabb = f.aabb.detach().float().cpu()
-        inv = f.invaabbSize.detach().float().cpu()
-        grid = [int(g) for g in (f.gridSize.tolist() if torch.is_tensor(f.gridSize) else f.gridSize)]
+        # box / grid scalars live in device tensors in the reference's module; they change only in
+        # update_stepSize / shrink, so the device->host reads (3 stream syncs) are cached on the tensors'
+        # identity instead of being paid by every render call
+        step_t = f.stepSize if torch.is_tensor(f.stepSize) else None
+        grid_t = f.gridSize if torch.is_tensor(f.gridSize) else None
+        if self.scalar_track.stale((f.aabb, f.invaabbSize, step_t, grid_t)) or self.scalars is None:
+            aabb = f.aabb.detach().float().cpu()
+            inv = f.invaabbSize.detach().float().cpu()
+            grid = [int(g) for g in (f.gridSize.tolist() if grid_t is not None else f.gridSize)]
+            self.scalars = ([float(aabb[0, a]) for a in range(3)], [float(aabb[1, a]) for a in range(3)],
+                            [float(inv[a]) for a in range(3)], grid,
+                            float(step_t.detach().float().cpu()) if step_t is not None else None)
+        lo_, hi_, inv_, grid, step_cached = self.scalars
+        if grid_t is None:
+            grid = [int(g) for g in f.gridSize]
         K = int(f.num_keyframes)
         for a in range(3):
-            s.aabb_min[a] = float(aabb[0, a])
-            s.aabb_max[a] = float(aabb[1, a])
-            s.inv_aabb[a] = float(inv[a])
+            s.aabb_min[a] = lo_[a]
+            s.aabb_max[a] = hi_[a]
+            s.inv_aabb[a] = inv_[a]
             s.grid[a] = grid[a]
         s.num_keyframes = K
         s.tmax = _f32(f.tmax)
         s.time_scale = _f32(f.tmax / (K - 1) if K > 1 else 1)
         s.dt_max = _f32(0.5 * f.tmax / (K - 1) if K > 1 else 1)
         s.near, s.far = _f32(f.near_far[0]), _f32(f.near_far[1])
-        s.step_size = float(f.stepSize.detach().float().cpu()) if torch.is_tensor(f.stepSize) else _f32(f.stepSize)
+        s.step_size = step_cached if step_t is not None else _f32(f.stepSize)
         s.n_samples = int(f.nSamples)
         s.density_shift = _f32(f.density_shift)
         s.distance_scale = _f32(f.distance_scale)
@@ -323,6 +371,7 @@ class FieldBinding:
         else:
             s.mask_layers = 0
             s.mask_dim = 3
+        s.mlp_mode = MLP_MODES[self.mlp_mode or _mlp_mode]
         return s
 
 
@@ -440,6 +489,7 @@ def render_backward(binding: FieldBinding, out: RenderOutputs, g_rgb, g_depth, g
     Returns gradients in the order of ``autograd._diff_params``."""
     lib = L.load()
     s = binding.s          # parameters are unchanged since forward (checked by the caller)
+    s.mlp_mode = MLP_MODES[binding.mlp_mode or _mlp_mode]
     a, b = out.args
     dev = out.weights.device
     n, S = out.weights.shape
@@ -521,7 +571,10 @@ def _counters(dev):
     return torch.empty(16, device=dev, dtype=torch.int32)
 
 
-def integrate_pos(binding: FieldBinding, x: torch.Tensor, t: torch.Tensor, base: torch.Tensor) -> torch.Tensor:
+def integrate_pos(binding: FieldBinding, x: torch.Tensor, t: torch.Tensor, base: torch.Tensor,
+                  group: Optional[bool] = None) -> torch.Tensor:
+    """``group``: sort the points by RK2 step count before tiling (True), never (False), or decide by
+    looking at the spread of the step counts (None; costs one device->host sync)."""
     s = binding.sync()
     x = x.detach().reshape(-1, 3).contiguous().float()
     n = x.shape[0]
@@ -535,9 +588,9 @@ def integrate_pos(binding: FieldBinding, x: torch.Tensor, t: torch.Tensor, base:
     # 1 step inside [0, tmax], up to 10 beyond) almost every random tile contains a 10-step point, so
     # the points are grouped by step count first; every point's arithmetic is unchanged.
     order = None
-    if n >= 4 * 128:
+    if n >= 4 * 128 and group is not False:
         steps = torch.ceil((t - base).abs() / float(s.dt_max)).to(torch.int32)
-        if int(steps.max()) > int(steps.min()) + 1:
+        if group or int(steps.max()) > int(steps.min()) + 1:
             order = torch.argsort(steps)
             x, t, base = x[order].contiguous(), t[order].contiguous(), base[order].contiguous()
     cnt = _counters(x.device)

@@ -131,6 +131,8 @@ class TensorVMKeyframeTimeKplane(nn.Module):
         self._binding = engine.FieldBinding(self)
         if self.use_vel:
             self.vel_net._binding = self._binding
+        # packed device copies are re-made after a state-dict load whatever the tensors' version counters say
+        self.register_load_state_dict_post_hook(lambda module, incompatible: engine.FieldBinding.invalidate())
 
     # ---------------------------------------------------------------- construction helpers
     @staticmethod
@@ -198,6 +200,11 @@ class TensorVMKeyframeTimeKplane(nn.Module):
     @property
     def binding(self) -> engine.FieldBinding:
         return self._binding
+
+    def invalidate_packed(self):
+        """Call after writing parameters through ``.data`` (which does not bump the version counter the
+        packed-copy cache keys on); see engine._Tracked."""
+        engine.FieldBinding.invalidate()
 
     # ---------------------------------------------------------------- coordinates
     def normalize_coord(self, xyz_sampled):
@@ -288,6 +295,7 @@ class TensorVMKeyframeTimeKplane(nn.Module):
                 time[i] = nn.Parameter(F.interpolate(time[i].data, size=(new_keyframes, res_target[n0]),
                                                      mode="bilinear", align_corners=True))
         self.update_stepSize(res_target, verbose=False)
+        engine.FieldBinding.invalidate()
 
     @torch.no_grad()
     def getDenseAlpha(self, gridSize=None, transfer=False):
@@ -316,6 +324,7 @@ class TensorVMKeyframeTimeKplane(nn.Module):
         alpha[alpha >= self.alphaMask_thres] = 1
         alpha[alpha < self.alphaMask_thres] = 0
         self.alphaMask = AlphaGridMask(self.device, self.aabb, alpha)
+        engine.FieldBinding.invalidate()
         valid_xyz = dense_xyz[alpha > 0.5]
         return torch.stack((valid_xyz.amin(0), valid_xyz.amax(0)))
 
@@ -342,6 +351,7 @@ class TensorVMKeyframeTimeKplane(nn.Module):
         newSize = b_r - t_l
         self.aabb = new_aabb
         self.update_stepSize((int(newSize[0]), int(newSize[1]), int(newSize[2])), verbose=False)
+        engine.FieldBinding.invalidate()
 
     # ---------------------------------------------------------------- rendering
     def render_rays(self, t, ray_o, ray_d, white_bg=True, transfer_vel=False, ray_chunk=None,

@@ -31,7 +31,7 @@ def occupancy_filter(field, points_n: torch.Tensor, t: torch.Tensor) -> torch.Te
         K = int(field.num_keyframes)
         tsf = field.tmax / (K - 1)
         base = torch.round((t / tsf).clamp(0.0, K - 1)) * tsf
-        prev = engine.integrate_pos(field.binding, points_n, t, base)
+        prev = engine.integrate_pos(field.binding, points_n, t, base, group=True)   # t ~ U(0, 1) per point
         xyzt = torch.cat([prev, field.normalize_time_coord(base)], dim=-1)
         sigma = engine.density_sigma(field.binding, xyzt)
         alpha = 1 - torch.exp(-sigma * 0.01 * 25)

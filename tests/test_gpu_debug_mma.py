@@ -20,7 +20,7 @@ def _tf32(x):
 
 def _run(At, G, lbo, sbo, kstep, layout, mn):
     from nvfi_b200 import _lib as L
-    lib = L.load()
+    lib = L.load_debug()
     D = torch.full((128, 128), float("nan"), device="cuda")
     rc = lib.nvfi_debug_mma_mn(At.data_ptr(), G.data_ptr(), D.data_ptr(), lbo, sbo, kstep, layout, mn,
                                torch.cuda.current_stream().cuda_stream)

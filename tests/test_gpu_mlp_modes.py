@@ -31,10 +31,10 @@ def mode(request):
 
 
 def test_default_mode_is_tensor_core():
-    from nvfi_b200 import _lib
+    from nvfi_b200 import engine
     import os
     if "NVFI_MLP_MODE" not in os.environ:
-        assert _lib.load().nvfi_get_mlp_mode() == _lib.MLP_F16X3
+        assert engine.get_mlp_mode() == "f16x3"
 
 
 def test_velocity_and_advection(g, model, mode):

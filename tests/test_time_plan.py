@@ -66,3 +66,21 @@ def test_no_velocity_field_never_advects():
     f = _field(use_vel=False)
     tt, base, tnb, advect = engine.time_plan(f, 0.33, False)
     assert not advect and tnb == pytest.approx(2 * 0.33 / 0.75 - 1, abs=1e-6)
+
+
+def test_packed_copy_cache_key_and_invalidate():
+    """engine._Tracked: in-place ops bump the version and make the key stale; a write
+    through .data does not — FieldBinding.invalidate() (called by load_state_dict / upsample / shrink /
+    updateAlphaMask) does."""
+    import torch
+    from nvfi_b200 import engine
+    p = torch.nn.Parameter(torch.zeros(4))
+    tr = engine._Tracked()
+    assert tr.stale((p,)) and not tr.stale((p,))
+    with torch.no_grad():
+        p.add_(1)
+    assert tr.stale((p,)) and not tr.stale((p,))
+    p.data.add_(1)                       # bypasses the version counter
+    assert not tr.stale((p,))
+    engine.FieldBinding.invalidate()
+    assert tr.stale((p,)) and not tr.stale((p,))

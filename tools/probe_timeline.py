@@ -26,7 +26,8 @@ step(); torch.cuda.synchronize()
 lib.nvfi_debug_timeline(None, 0)
 b = buf.cpu().tolist()
 half = len(b) // 2
-h16 = lib.nvfi_get_mlp_mode() == L.MLP_F16X3
+from nvfi_b200 import engine
+h16 = engine.get_mlp_mode() == "f16x3"
 parts = [("worker thread 0", b[:half]), ("issuer warp", b[half:])] if h16 else [("thread 0", b)]
 for who, bb in parts:
     ev = [(bb[i], bb[i + 1]) for i in range(0, len(bb), 2) if bb[i + 1] != 0]
