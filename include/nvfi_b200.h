@@ -205,6 +205,21 @@ typedef struct NvfiRenderGrads {
   int64_t workspace_bytes; /* >= nvfi_backward_workspace_bytes() */
 } NvfiRenderGrads;
 
+/* Destinations of nvfi_unpack_render_grads, in the PARAMETER layouts of the reference module (what
+ * autograd hands to the optimiser): planes (1, R, H, W), nn.Linear weights (out, in), biases (out).
+ * A NULL pointer skips that tensor. */
+typedef struct NvfiParamGrads {
+  float* dplane_space[3];
+  float* dplane_time[3];
+  float* aplane_space[3];
+  float* aplane_time[3];
+  float* basis_mat;
+  float* render_w[3];
+  float* render_b[3];
+  float* vel_w[NVFI_VEL_LAYERS];
+  float* vel_b[NVFI_VEL_LAYERS];
+} NvfiParamGrads;
+
 /* Gradient accumulators of nvfi_pde_loss, in the packed layouts of NvfiLinear.wt / bias
  * (convert with nvfi_unpack_linear).  All g_* must be zero-initialised by the caller. */
 typedef struct NvfiPdeGrads {
@@ -278,6 +293,13 @@ int nvfi_render_forward(const NvfiField* field, const NvfiRenderArgs* args,
 int nvfi_render_backward(const NvfiField* field, const NvfiRenderArgs* args,
                          const NvfiRenderBuffers* buf, const NvfiRenderGrads* grads,
                          void* stream);
+
+/* All packed gradient accumulators of a backward pass -> parameter layouts, in TWO launches (one
+ * batched tiled transpose for the 12 planes, one batched un-padding transpose for the linear layers)
+ * instead of one launch per tensor: at the shipped 2 048-ray training batch the per-tensor launches
+ * were a tenth of the iteration. */
+int nvfi_unpack_render_grads(const NvfiField* field, const NvfiRenderGrads* grads,
+                             const NvfiParamGrads* out, void* stream);
 
 /* Host-buffer variant of the eval render (the end-to-end entry point): rays and
  * jitter come from HOST memory, rgb/depth/acc are copied back to HOST memory; the

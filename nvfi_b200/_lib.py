@@ -86,6 +86,14 @@ class NvfiRenderGrads(C.Structure):
     ]
 
 
+class NvfiParamGrads(C.Structure):
+    _fields_ = [
+        ("dplane_space", P3), ("dplane_time", P3), ("aplane_space", P3), ("aplane_time", P3),
+        ("basis_mat", C.c_void_p), ("render_w", P3), ("render_b", P3),
+        ("vel_w", C.c_void_p * VEL_LAYERS), ("vel_b", C.c_void_p * VEL_LAYERS),
+    ]
+
+
 class NvfiPdeGrads(C.Structure):
     _fields_ = [
         ("g_vel_w", C.c_void_p * VEL_LAYERS), ("g_vel_b", C.c_void_p * VEL_LAYERS),
@@ -119,6 +127,8 @@ SIGNATURES = {
                                  C.POINTER(NvfiRenderBuffers), _vp]),
     "nvfi_render_backward": (_i, [C.POINTER(NvfiField), C.POINTER(NvfiRenderArgs),
                                   C.POINTER(NvfiRenderBuffers), C.POINTER(NvfiRenderGrads), _vp]),
+    "nvfi_unpack_render_grads": (_i, [C.POINTER(NvfiField), C.POINTER(NvfiRenderGrads),
+                                      C.POINTER(NvfiParamGrads), _vp]),
     "nvfi_render_forward_host": (_i, [C.POINTER(NvfiField), C.POINTER(NvfiRenderArgs), _vp, _vp,
                                       _vp, _vp, _vp, _vp, C.POINTER(NvfiRenderBuffers), _vp, _vp,
                                       _vp, _vp]),

@@ -1,6 +1,8 @@
 // C-ABI entry points (include/nvfi_b200.h): layout packing, ray generation and the
 // forward-render orchestration.  Every function validates its arguments, enqueues
 // kernels on the caller's stream and returns an error code; nothing here touches torch.
+#include <cstring>
+
 #include <cuda_fp16.h>
 
 #include "nvfi_common.cuh"
@@ -33,6 +35,59 @@ __global__ void k_transpose(const float* __restrict__ src, float* __restrict__ d
     const int r = r0 + threadIdx.x;
     if (r < rows && c < cols) dst[c * rows + r] = tile[threadIdx.x][j];
   }
+}
+
+// Up to 12 (rows, cols) -> (cols, rows) transposes in one launch: blockIdx.z selects the job; blocks
+// outside a job's extent exit.
+struct TransposeJob {
+  const float* src;
+  float* dst;
+  int rows;
+  long long cols;
+};
+struct TransposeBatch {
+  TransposeJob job[12];
+};
+__global__ void k_transpose_batch(const __grid_constant__ TransposeBatch tb) {
+  const TransposeJob& J = tb.job[blockIdx.z];
+  if (J.src == nullptr) return;
+  __shared__ float tile[32][33];
+  const long long c0 = (long long)blockIdx.x * 32;
+  const int r0 = blockIdx.y * 32;
+  if (c0 >= J.cols || r0 >= J.rows) return;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j;
+    const long long c = c0 + threadIdx.x;
+    if (r < J.rows && c < J.cols) tile[j][threadIdx.x] = J.src[(long long)r * J.cols + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long c = c0 + j;
+    const int r = r0 + threadIdx.x;
+    if (r < J.rows && c < J.cols) J.dst[c * J.rows + r] = tile[threadIdx.x][j];
+  }
+}
+
+// Up to 10 packed (k_pad, n_pad) [+ (n_pad)] -> nn.Linear (out, in) [+ (out)] in one launch.
+struct UnpackJob {
+  const float* wt;
+  const float* bias_in;
+  float* w;
+  float* b;
+  int out_dim, in_dim, n_pad;
+};
+struct UnpackBatch {
+  UnpackJob job[10];
+};
+__global__ void k_unpack_linear_batch(const __grid_constant__ UnpackBatch ub) {
+  const UnpackJob& J = ub.job[blockIdx.y];
+  if (J.wt == nullptr) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < J.out_dim * J.in_dim) {
+    const int n = i / J.in_dim, k = i - n * J.in_dim;
+    J.w[i] = J.wt[k * J.n_pad + n];
+  }
+  if (J.b && J.bias_in && i < J.out_dim) J.b[i] = J.bias_in[i];
 }
 
 // nn.Linear (out,in) -> W^T zero-padded (k_pad, n_pad)
@@ -151,6 +206,66 @@ extern "C" int nvfi_unpack_plane(const float* src_hwc, float* dst_nchw, int r, i
   dim3 grid((unsigned)((r + 31) / 32), (unsigned)((hw + 31) / 32));
   NVFI_LAUNCH(k_transpose, grid, block, 0, (cudaStream_t)stream, src_hwc, dst_nchw, (int)hw, r);
   return (int)cudaGetLastError();
+}
+
+extern "C" int nvfi_unpack_render_grads(const NvfiField* F, const NvfiRenderGrads* D, const NvfiParamGrads* P,
+                                        void* stream) {
+  if (!F || !D || !P) return NVFI_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  // ---- planes: packed (H*W, R) -> (R, H*W)
+  TransposeBatch tb;
+  memset(&tb, 0, sizeof(tb));
+  long long max_hw = 0;
+  int max_r = 0, nj = 0;
+  const int K = F->num_keyframes;
+  for (int k = 0; k < 3; ++k) {
+    // space plane k: H = grid[m1], W = grid[m0]; time plane k: H = K, W = grid[n0]  (include/nvfi_b200.h)
+    const int m0 = (k == 2) ? 1 : 0, m1 = (k == 0) ? 1 : 2, n0 = 2 - k;
+    const long long hw_s = (long long)F->grid[m1] * F->grid[m0], hw_t = (long long)K * F->grid[n0];
+    const struct {
+      const float* src;
+      float* dst;
+      long long hw;
+      int r;
+    } e[4] = {{D->g_dplane_space[k], P->dplane_space[k], hw_s, F->rd},
+              {D->g_dplane_time[k], P->dplane_time[k], hw_t, F->rd},
+              {D->g_aplane_space[k], P->aplane_space[k], hw_s, F->ra},
+              {D->g_aplane_time[k], P->aplane_time[k], hw_t, F->ra}};
+    for (int j = 0; j < 4; ++j) {
+      if (!e[j].src || !e[j].dst) continue;
+      if (e[j].hw > 0x7fffffffLL) return NVFI_EUNSUPPORTED;
+      tb.job[nj++] = TransposeJob{e[j].src, e[j].dst, (int)e[j].hw, (long long)e[j].r};
+      if (e[j].hw > max_hw) max_hw = e[j].hw;
+      if (e[j].r > max_r) max_r = e[j].r;
+    }
+  }
+  if (nj > 0) {
+    dim3 block(32, 8);
+    dim3 grid((unsigned)((max_r + 31) / 32), (unsigned)((max_hw + 31) / 32), 12);
+    if (grid.y > 65535u) return NVFI_EUNSUPPORTED;
+    NVFI_LAUNCH(k_transpose_batch, grid, block, 0, st, tb);
+    NVFI_CUDA_OK(cudaGetLastError());
+  }
+  // ---- linear layers
+  UnpackBatch ub;
+  memset(&ub, 0, sizeof(ub));
+  int nl = 0, max_n = 0;
+  auto add = [&](const NvfiLinear& L, const float* wt, const float* bi, float* w, float* b) {
+    if (!wt || !w) return;
+    ub.job[nl++] = UnpackJob{wt, bi, w, b, L.out_dim, L.in_dim, L.n_pad};
+    if (L.out_dim * L.in_dim > max_n) max_n = L.out_dim * L.in_dim;
+  };
+  add(F->basis_mat, D->g_basis_mat, nullptr, P->basis_mat, nullptr);
+  if (F->shading_mode == NVFI_SHADING_MLP_PE)
+    for (int i = 0; i < 3; ++i) add(F->render_mlp[i], D->g_render_w[i], D->g_render_b[i], P->render_w[i], P->render_b[i]);
+  if (F->use_vel)
+    for (int l = 0; l < NVFI_VEL_LAYERS; ++l) add(F->vel_net[l], D->g_vel_w[l], D->g_vel_b[l], P->vel_w[l], P->vel_b[l]);
+  if (nl > 0) {
+    dim3 grid((unsigned)((max_n + 255) / 256), 10);
+    NVFI_LAUNCH(k_unpack_linear_batch, grid, 256, 0, st, ub);
+    NVFI_CUDA_OK(cudaGetLastError());
+  }
+  return NVFI_OK;
 }
 
 extern "C" int nvfi_pack_linear(const float* w, const float* b, float* wt, float* bias_out,

@@ -505,31 +505,62 @@ def render_backward(binding: FieldBinding, out: RenderOutputs, g_rgb, g_depth, g
     g_acc, g_w = cg(g_acc, (n,)), cg(g_w, (n, S))
     d = L.NvfiRenderGrads()
     d.g_rgb, d.g_depth, d.g_acc, d.g_weights = _ptr(g_rgb), _ptr(g_depth), _ptr(g_acc), _ptr(g_w)
-    keep = []
-    gp = {}
-    for name, dst in (("density_plane_space", d.g_dplane_space), ("density_plane_time", d.g_dplane_time),
-                      ("app_plane_space", d.g_aplane_space), ("app_plane_time", d.g_aplane_time)):
-        gp[name] = []
+    mlp_mode = s.shading_mode == L.SHADING_MLP_PE
+    advected = bool(a.advect) and bool(s.use_vel)
+    # ONE zero-filled buffer for every packed gradient accumulator and ONE buffer for the gradients in the
+    # parameter layouts (a memset and two batched launches instead of ~30 fills and 22 transposes)
+    plane_names = ("density_plane_space", "density_plane_time", "app_plane_space", "app_plane_time")
+    sizes = []          # (packed numel, out shape)
+    for name in plane_names:
         for k in range(3):
             R, H, W = binding.planes[name][k].shape
-            g = torch.zeros(H, W, R, **f32)
-            gp[name].append(g)
-            dst[k] = g.data_ptr()
-    g_basis = torch.zeros_like(binding.basis.wt)
-    d.g_basis_mat = g_basis.data_ptr()
-    g_rw, g_rb = [], []
-    mlp_mode = s.shading_mode == L.SHADING_MLP_PE
+            sizes.append((H * W * R, (1, R, H, W)))
+    lin = [(binding.basis, False)]
     if mlp_mode:
-        for i in range(3):
-            g_rw.append(torch.zeros_like(binding.render[i].wt))
-            g_rb.append(torch.zeros_like(binding.render[i].bias))
-            d.g_render_w[i], d.g_render_b[i] = g_rw[i].data_ptr(), g_rb[i].data_ptr()
-    g_vw, g_vb = [], []
+        lin += [(binding.render[i], True) for i in range(3)]
+    if s.use_vel:
+        lin += [(binding.vel[j], True) for j in range(L.VEL_LAYERS)]
+    for pl, has_b in lin:
+        sizes.append((pl.wt.numel(), (pl.out_dim, pl.in_dim)))
+        if has_b:
+            sizes.append((pl.bias.numel(), (pl.out_dim,)))
+    al = lambda x: (x + 31) // 32 * 32      # 128-byte alignment of every slice
+    packed = torch.zeros(sum(al(n) for n, _ in sizes), **f32)
+    outbuf = torch.empty(sum(al(math.prod(sh)) for _, sh in sizes), **f32)
+    pk, ov = [], []
+    po = oo = 0
+    for n_, sh in sizes:
+        pk.append(packed[po:po + n_])
+        po += al(n_)
+        m_ = math.prod(sh)
+        ov.append(outbuf[oo:oo + m_].view(sh))
+        oo += al(m_)
+    P = L.NvfiParamGrads()
+    it = iter(range(len(sizes)))
+    for dst, pdst in ((d.g_dplane_space, P.dplane_space), (d.g_dplane_time, P.dplane_time),
+                      (d.g_aplane_space, P.aplane_space), (d.g_aplane_time, P.aplane_time)):
+        for k in range(3):
+            i = next(it)
+            dst[k], pdst[k] = pk[i].data_ptr(), ov[i].data_ptr()
+    grads_idx = list(range(12))
+    i = next(it)
+    d.g_basis_mat, P.basis_mat = pk[i].data_ptr(), ov[i].data_ptr()
+    grads_idx.append(i)
+    if mlp_mode:
+        for r in range(3):
+            iw, ib = next(it), next(it)
+            d.g_render_w[r], d.g_render_b[r] = pk[iw].data_ptr(), pk[ib].data_ptr()
+            P.render_w[r], P.render_b[r] = ov[iw].data_ptr(), ov[ib].data_ptr()
+            grads_idx += [iw, ib]
     if s.use_vel:
         for j in range(L.VEL_LAYERS):
-            g_vw.append(torch.zeros_like(binding.vel[j].wt))
-            g_vb.append(torch.zeros_like(binding.vel[j].bias))
-            d.g_vel_w[j], d.g_vel_b[j] = g_vw[j].data_ptr(), g_vb[j].data_ptr()
+            iw, ib = next(it), next(it)
+            d.g_vel_w[j], d.g_vel_b[j] = pk[iw].data_ptr(), pk[ib].data_ptr()
+            if advected:
+                P.vel_w[j], P.vel_b[j] = ov[iw].data_ptr(), ov[ib].data_ptr()
+                grads_idx += [iw, ib]
+            else:   # keyframe render: the velocity net is not on the graph (reference: grad None)
+                grads_idx += [None, None]
     g_x = torch.empty(n, S, 3, **f32)
     g_sig = torch.empty(n, S, **f32)
     g_eff = torch.empty(n, 3, **f32)
@@ -539,27 +570,12 @@ def render_backward(binding: FieldBinding, out: RenderOutputs, g_rgb, g_depth, g
     d.workspace, d.workspace_bytes = ws.data_ptr(), ws_bytes
     L.check(lib.nvfi_render_backward(C.byref(s), C.byref(a), C.byref(b), C.byref(d), _stream()),
             "render_backward")
+    L.check(lib.nvfi_unpack_render_grads(C.byref(s), C.byref(d), C.byref(P), _stream()), "unpack_render_grads")
     global LAST_BWD_COUNTERS
     LAST_BWD_COUNTERS = out.counters
     if DEBUG_KEEP is not None:
         DEBUG_KEEP.update(g_sigma=g_sig, g_x_adv=g_x, g_rgb_eff=g_eff, fwd=out)
-    grads: List[Optional[torch.Tensor]] = []
-    for name in ("density_plane_space", "density_plane_time", "app_plane_space", "app_plane_time"):
-        for k in range(3):
-            grads.append(binding.planes[name][k].unpack_grad(gp[name][k]))
-    grads.append(binding.basis.unpack_grad(g_basis, None, False)[0])
-    if mlp_mode:
-        for i in range(3):
-            gw, gb = binding.render[i].unpack_grad(g_rw[i], g_rb[i], True)
-            grads += [gw, gb]
-    if s.use_vel:
-        advected = bool(a.advect)
-        for j in range(L.VEL_LAYERS):
-            if advected:
-                gw, gb = binding.vel[j].unpack_grad(g_vw[j], g_vb[j], True)
-            else:   # keyframe render: the velocity net is not on the graph (reference: grad None)
-                gw, gb = None, None
-            grads += [gw, gb]
+    grads: List[Optional[torch.Tensor]] = [None if i is None else ov[i] for i in grads_idx]
     assert len(grads) == len(needs), (len(grads), len(needs))
     return [g if need else None for g, need in zip(grads, needs)]
 

@@ -46,10 +46,12 @@ def test_struct_layouts_match_c():
         pytest.skip("gcc not available")
     probes = [("NvfiLinear", _lib.NvfiLinear, ["umma", "ummaT", "in_dim", "ummaT_rows"]),
               ("NvfiField", _lib.NvfiField, ["grid", "dplane_space", "basis_mat", "vel_net", "gate_lo",
-                                             "alpha_volume", "mask_net"]),
+                                             "alpha_volume", "mask_net", "mlp_mode"]),
               ("NvfiRenderArgs", _lib.NvfiRenderArgs, ["jitter", "chunk_bg", "t", "advect"]),
               ("NvfiRenderBuffers", _lib.NvfiRenderBuffers, ["x_adv", "sigma", "stats"]),
               ("NvfiRenderGrads", _lib.NvfiRenderGrads, ["g_basis_mat", "g_vel_b", "workspace_bytes"]),
+              ("NvfiParamGrads", _lib.NvfiParamGrads, ["aplane_time", "basis_mat", "render_b", "vel_b"]),
+              ("NvfiPdeGrads", _lib.NvfiPdeGrads, ["g_acc_w", "g_acc_pts", "workspace_bytes"]),
               ("NvfiProfileEntry", _lib.NvfiProfileEntry, ["ms", "launches"])]
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for name, _, fields in probes:
