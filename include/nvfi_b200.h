@@ -362,6 +362,14 @@ int nvfi_tv_loss(const float* plane, int C, int H, int W, int time_plane, float 
 int nvfi_l1_loss(const float* plane, int64_t n, float offset, float scale, double* loss_accum,
                  float* grad, void* stream);
 
+/* ---- segmentation trainer (next-row f4 of SURVEY.md section 8; not on the render path) --------------
+ * K nearest neighbours of every query point among `points`, per batch element: replaces
+ * pytorch3d.ops.knn_points as called by smooth_loss (utils/seg_loss.py:78-90).  query (batch, n_query, 3),
+ * points (batch, n_points, 3); dist (batch, n_query, k) SQUARED L2 distances in ascending order, idx
+ * (batch, n_query, k) int64 (-1 where fewer than k points exist).  k in {1, 2, 4, 8, 16}. */
+int nvfi_knn_points(const float* query, const float* points, int32_t batch, int32_t n_query,
+                    int32_t n_points, int32_t k, float* dist, int64_t* idx, void* stream);
+
 /* Development aid: (tag, clock64) pairs recorded by CTA 0 of the tensor-core backward at its phase
  * boundaries into dev_buf (cap int64 entries); NULL disables. */
 int nvfi_debug_timeline(long long* dev_buf, int cap);

@@ -139,6 +139,7 @@ SIGNATURES = {
     "nvfi_app_feature": (_i, [C.POINTER(NvfiField), _vp, _i64, _vp, _vp, _vp]),
     "nvfi_velocity": (_i, [C.POINTER(NvfiField), _vp, _i64, _i, _vp, _vp, _vp]),
     "nvfi_debug_timeline": (_i, [_vp, _i]),
+    "nvfi_knn_points": (_i, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp]),
     "nvfi_tv_loss": (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "nvfi_l1_loss": (_i, [_vp, _i64, _f, _f, _vp, _vp, _vp]),
     "nvfi_pde_loss": (_i, [C.POINTER(NvfiField), _vp, _vp, _i64, _vp, C.POINTER(NvfiPdeGrads), _i, _vp, _vp]),
