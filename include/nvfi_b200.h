@@ -232,6 +232,14 @@ typedef struct NvfiPdeGrads {
   int64_t workspace_bytes;
 } NvfiPdeGrads;
 
+/* Destinations of nvfi_unpack_pde_grads: nn.Linear layouts (out, in) / (out) of both weight nets. */
+typedef struct NvfiPdeParamGrads {
+  float* vel_w[NVFI_VEL_LAYERS];
+  float* vel_b[NVFI_VEL_LAYERS];
+  float* acc_w[NVFI_VEL_LAYERS];
+  float* acc_b[NVFI_VEL_LAYERS];
+} NvfiPdeParamGrads;
+
 /* ---- library info --------------------------------------------------------------- */
 int nvfi_abi_version(void);
 /* Bytes of `workspace` scratch nvfi_render_backward needs on the current device. */
@@ -300,6 +308,10 @@ int nvfi_render_backward(const NvfiField* field, const NvfiRenderArgs* args,
  * were a tenth of the iteration. */
 int nvfi_unpack_render_grads(const NvfiField* field, const NvfiRenderGrads* grads,
                              const NvfiParamGrads* out, void* stream);
+
+/* The 24 packed gradient accumulators of nvfi_pde_loss -> nn.Linear layouts in one launch. */
+int nvfi_unpack_pde_grads(const NvfiField* field, const NvfiPdeGrads* grads, const NvfiPdeParamGrads* out,
+                          void* stream);
 
 /* Host-buffer variant of the eval render (the end-to-end entry point): rays and
  * jitter come from HOST memory, rgb/depth/acc are copied back to HOST memory; the

@@ -102,6 +102,13 @@ class NvfiPdeGrads(C.Structure):
     ]
 
 
+class NvfiPdeParamGrads(C.Structure):
+    _fields_ = [
+        ("vel_w", C.c_void_p * VEL_LAYERS), ("vel_b", C.c_void_p * VEL_LAYERS),
+        ("acc_w", C.c_void_p * VEL_LAYERS), ("acc_b", C.c_void_p * VEL_LAYERS),
+    ]
+
+
 class NvfiProfileEntry(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("ms", C.c_double), ("launches", C.c_int64)]
 
@@ -129,6 +136,7 @@ SIGNATURES = {
                                   C.POINTER(NvfiRenderBuffers), C.POINTER(NvfiRenderGrads), _vp]),
     "nvfi_unpack_render_grads": (_i, [C.POINTER(NvfiField), C.POINTER(NvfiRenderGrads),
                                       C.POINTER(NvfiParamGrads), _vp]),
+    "nvfi_unpack_pde_grads": (_i, [C.POINTER(NvfiField), C.POINTER(NvfiPdeGrads), C.POINTER(NvfiPdeParamGrads), _vp]),
     "nvfi_render_forward_host": (_i, [C.POINTER(NvfiField), C.POINTER(NvfiRenderArgs), _vp, _vp,
                                       _vp, _vp, _vp, _vp, C.POINTER(NvfiRenderBuffers), _vp, _vp,
                                       _vp, _vp]),

@@ -68,7 +68,7 @@ __global__ void k_transpose_batch(const __grid_constant__ TransposeBatch tb) {
   }
 }
 
-// Up to 10 packed (k_pad, n_pad) [+ (n_pad)] -> nn.Linear (out, in) [+ (out)] in one launch.
+// Up to 12 packed (k_pad, n_pad) [+ (n_pad)] -> nn.Linear (out, in) [+ (out)] in one launch.
 struct UnpackJob {
   const float* wt;
   const float* bias_in;
@@ -77,7 +77,7 @@ struct UnpackJob {
   int out_dim, in_dim, n_pad;
 };
 struct UnpackBatch {
-  UnpackJob job[10];
+  UnpackJob job[12];
 };
 __global__ void k_unpack_linear_batch(const __grid_constant__ UnpackBatch ub) {
   const UnpackJob& J = ub.job[blockIdx.y];
@@ -261,8 +261,37 @@ extern "C" int nvfi_unpack_render_grads(const NvfiField* F, const NvfiRenderGrad
   if (F->use_vel)
     for (int l = 0; l < NVFI_VEL_LAYERS; ++l) add(F->vel_net[l], D->g_vel_w[l], D->g_vel_b[l], P->vel_w[l], P->vel_b[l]);
   if (nl > 0) {
-    dim3 grid((unsigned)((max_n + 255) / 256), 10);
+    dim3 grid((unsigned)((max_n + 255) / 256), 12);
     NVFI_LAUNCH(k_unpack_linear_batch, grid, 256, 0, st, ub);
+    NVFI_CUDA_OK(cudaGetLastError());
+  }
+  return NVFI_OK;
+}
+
+extern "C" int nvfi_unpack_pde_grads(const NvfiField* F, const NvfiPdeGrads* G, const NvfiPdeParamGrads* P,
+                                     void* stream) {
+  if (!F || !G || !P) return NVFI_EINVAL;
+  UnpackBatch ub;
+  memset(&ub, 0, sizeof(ub));
+  int nl = 0, max_n = 0;
+  for (int l = 0; l < NVFI_VEL_LAYERS; ++l) {
+    const struct {
+      const NvfiLinear& L;
+      const float* wt;
+      const float* bi;
+      float* w;
+      float* b;
+    } e[2] = {{F->vel_net[l], G->g_vel_w[l], G->g_vel_b[l], P->vel_w[l], P->vel_b[l]},
+              {F->acc_net[l], G->g_acc_w[l], G->g_acc_b[l], P->acc_w[l], P->acc_b[l]}};
+    for (int j = 0; j < 2; ++j) {
+      if (!e[j].wt || !e[j].w) continue;
+      ub.job[nl++] = UnpackJob{e[j].wt, e[j].bi, e[j].w, e[j].b, e[j].L.out_dim, e[j].L.in_dim, e[j].L.n_pad};
+      if (e[j].L.out_dim * e[j].L.in_dim > max_n) max_n = e[j].L.out_dim * e[j].L.in_dim;
+    }
+  }
+  if (nl > 0) {
+    dim3 grid((unsigned)((max_n + 255) / 256), 12);
+    NVFI_LAUNCH(k_unpack_linear_batch, grid, 256, 0, (cudaStream_t)stream, ub);
     NVFI_CUDA_OK(cudaGetLastError());
   }
   return NVFI_OK;

@@ -29,6 +29,8 @@
 // FP16 range: the upstream gradient of a tile is scaled by a power of two so that its largest
 // component is in [8, 16) (12 binades of headroom for growth through the layers, 2^-29 of the tile
 // maximum as absolute resolution); every result is unscaled when it leaves the tensor cores.
+#include <cstring>
+
 #include "backward_common.cuh"
 
 #ifdef NVFI_TIMELINE
@@ -85,6 +87,7 @@ struct BwdTile {
   int warp_cnt[2][NT / 32];
   int batch;
   unsigned gmax;            // bits of the largest |upstream gradient| of the tile
+  unsigned gmax_l[2];       // JVP: the same per layer (ping-pong)
   th::Issuer iss;           // weight-ring state of the issuer warp between calls
 };
 
@@ -129,12 +132,18 @@ __device__ __forceinline__ float colsum8(const float v[8], int lane) {
 // stash_a / stash_s = that evaluation's stash; (xs, ys, zs)[m] = its input.  Out: T.gout[0..2][m] =
 // dL/d(x, y, z) through the network input; weight gradients added to the packed gradient buffers, bias
 // and head gradients to the register accumulators.  Whole CTA (13 block barriers).
+// JVP = 1: the reverse pass of the forward-mode evaluation of the PDE loss (mlp_h.cuh, k_pde_jac_h): rows
+// are 6 points x (value + 4 tangents) per lane quadrant; the activation step couples the rows of a point,
+//     g_h0 = g_a0 S + sum_j g_aj S2_j,   g_hj = g_aj S        (S = silu'(h_0), S2_j = silu''(h_0) h_j),
+// bias gradients come from the value rows only and no input gradient is produced.
+template <int JVP = 0>
 __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint32_t tA, uint32_t tG,
                            const NvfiRenderGrads& D, const unsigned char* __restrict__ stash_a,
                            const float* __restrict__ stash_s, const float* xs, const float* ys, const float* zs,
                            uint32_t& dphase, uint32_t& wphase, uint32_t& aphase, float (&acc_head)[6],
-                           float (&acc_bias)[6]) {
+                           float (&acc_bias)[6], const float* __restrict__ stash_s2 = nullptr) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool value_row = !JVP || (lane < 30 && lane % 5 == 0);
   const uint32_t gw_hi = tc::smem_u32(T.gw_hi), gw_lo = tc::smem_u32(T.gw_lo);
 
   // ---- scale of the tile: largest |dL/dw| -> [8, 16)
@@ -308,7 +317,7 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
     th::st_shared_v4(gw_lo + off + 128u, z);
     th::fence_async_smem();
   }
-  if (warp < 6)     // db5[n] = sum_m gout[n][m]: warp n, each lane 4 samples (reduced at kernel end)
+  if (warp < 6 && value_row)   // db5[n] = sum_m gout[n][m]: warp n, each lane 4 samples (reduced at kernel end)
     acc_bias[5] += T.gout[warp][lane] + T.gout[warp][lane + 32] + T.gout[warp][lane + 64] + T.gout[warp][lane + 96];
   tc::tc_fence_before();
   NVFI_TLH(100, 0);
@@ -327,8 +336,10 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
     }
   };
   load_s(4);
+  float inv_cum = inv_scale;   // JVP: 1 / (cumulative scale of G_L), updated layer by layer
 #pragma unroll 1
   for (int L = 5; L >= 0; --L) {
+    const float inv_L = JVP ? inv_cum : inv_scale;   // un-scaling of this layer's weight gradient
     NVFI_TLH(110 + L, 0);
     tc::mbar_wait(&c.dbar, dphase & 1);   // D0 = dX(L)
     ++dphase;
@@ -343,20 +354,73 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
 #pragma unroll
       for (int g = 0; g < 4; ++g) tc::tmem_ld8_nowait(dcol + 32u * g, raw[g]);
       tc::tmem_ld_wait();
+      if (!JVP) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float s8[8] = {sv[g][0].x, sv[g][0].y, sv[g][0].z, sv[g][0].w, sv[g][1].x, sv[g][1].y, sv[g][1].z, sv[g][1].w};
-        float v[8];
+        for (int g = 0; g < 4; ++g) {
+          const float s8[8] = {sv[g][0].x, sv[g][0].y, sv[g][0].z, sv[g][0].w, sv[g][1].x, sv[g][1].y, sv[g][1].z, sv[g][1].w};
+          float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[g][i]) * s8[i];
-        th::split8(v, ghi[g], glo[g]);
-        // bias gradient of layer L - 1: column sums of G_{L-1} over the warp's 32 samples; lane j keeps
-        // column 32 (j >> 3) + 8 h + (j & 7)
-        const float cs = colsum8(v, lane);
-        if ((lane >> 3) == g) bsum = cs;
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[g][i]) * s8[i];
+          th::split8(v, ghi[g], glo[g]);
+          // bias gradient of layer L - 1: column sums of G_{L-1} over the warp's 32 samples; lane j keeps
+          // column 32 (j >> 3) + 8 h + (j & 7)
+          const float cs = colsum8(v, lane);
+          if ((lane >> 3) == g) bsum = cs;
+        }
+      } else {
+        // forward-mode rows: the value row collects the second-order terms of its 4 tangent rows, and the
+        // tile is RE-SCALED per layer (power of two, largest |G_{L-1}| -> [8, 16)): the adjoints of a PDE
+        // tile span many binades (one point with a large residual sets the head's scale) and shrink by
+        // ~0.3 per layer, and FP16 hi + lo only resolves 2^-25 of the scaled values in absolute terms
+        float vv[4][8];
+        float mx = 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float s8[8] = {sv[g][0].x, sv[g][0].y, sv[g][0].z, sv[g][0].w, sv[g][1].x, sv[g][1].y, sv[g][1].z, sv[g][1].w};
+          const float4* sp2 = reinterpret_cast<const float4*>(stash_s2) + ((size_t)(L - 1) * 32 + h * 2 + g * 8) * NVFI_TM + m;
+          const float4 q0 = ldcg4_now(sp2), q1 = ldcg4_now(sp2 + NVFI_TM);
+          const float t8[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float ga = __uint_as_float(raw[g][i]);
+            const float cj = ga * t8[i];
+            const float u = cj + __shfl_down_sync(0xffffffffu, cj, 1);
+            const float cross = __shfl_down_sync(0xffffffffu, u, 1) + __shfl_down_sync(0xffffffffu, u, 3);
+            vv[g][i] = fmaf(ga, s8[i], value_row ? cross : 0.f);
+            mx = fmaxf(mx, fabsf(vv[g][i]));
+          }
+        }
+        if (tid == 0) T.gmax_l[(L & 1) ^ 1] = 0u;   // next layer's slot (its last readers passed barrier (C1))
+        const unsigned bw = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+        if (lane == 0 && bw) atomicMax(&T.gmax_l[L & 1], bw);
+        asm volatile("bar.sync 1, 512;" ::: "memory");   // the 16 worker warps
+        float f = 1.f, finv = 1.f;
+        {
+          const unsigned bm = T.gmax_l[L & 1];
+          if (bm) {
+            unsigned ex = bm >> 23;
+            ex = ex < 30u ? 30u : (ex > 250u ? 250u : ex);
+            f = __uint_as_float((257u - ex) << 23);
+            finv = __uint_as_float((ex - 3u) << 23);
+          }
+        }
+        inv_cum *= finv;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = vv[g][i] * f;
+          th::split8(v, ghi[g], glo[g]);
+          if (!value_row) {   // bias gradients come from the value rows only
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+          }
+          const float cs = colsum8(v, lane);
+          if ((lane >> 3) == g) bsum = cs;
+        }
       }
-      acc_bias[L - 1] = fmaf(bsum, inv_scale, acc_bias[L - 1]);
-    } else if (h == 0) {
+      acc_bias[L - 1] = fmaf(bsum, JVP ? inv_cum : inv_scale, acc_bias[L - 1]);
+    } else if (!JVP && h == 0) {
       // dL/d(encoding) -> dL/d(x, y, z)  (encoder tangents)
       float ge[32];
       tc::tmem_ld32(tb + lane_base + kColD0, ge);
@@ -383,6 +447,7 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
     // CTAs (which run out of phase) stays near half of 148 x 608 KB.
     if (L >= 1) {   // 64 KB = 512 lines each: one line per worker thread
       discard_l2(reinterpret_cast<const unsigned char*>(stash_s) + (size_t)(L - 1) * 65536 + (size_t)tid * 128);
+      if (JVP) discard_l2(reinterpret_cast<const unsigned char*>(stash_s2) + (size_t)(L - 1) * 65536 + (size_t)tid * 128);
       if (L <= 4) discard_l2(stash_a + 32768 + (size_t)(L - 1) * th::kTileBytes + (size_t)tid * 128);
     } else if (tid < 256) {
       discard_l2(stash_a + (size_t)tid * 128);   // the encoding (hi | lo slab 0)
@@ -407,7 +472,7 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
         tc::tmem_ld8_nowait(tb + lane_base + kColDh, r);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int n = 0; n < 6; ++n) acc_head[n] = fmaf(__uint_as_float(r[n]), inv_scale, acc_head[n]);
+        for (int n = 0; n < 6; ++n) acc_head[n] = fmaf(__uint_as_float(r[n]), inv_L, acc_head[n]);
       }
       continue;
     }
@@ -421,7 +486,7 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
         float dv[16];
         tc::tmem_ld16(tb + lane_base + kColD1 + 128u * (uint32_t)(L & 1) + (uint32_t)(h * 32 + half * 16), dv);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) red_add(pp + (size_t)(half * 16 + i) * NVFI_TM, dv[i] * inv_scale);
+        for (int i = 0; i < 16; ++i) red_add(pp + (size_t)(half * 16 + i) * NVFI_TM, dv[i] * inv_L);
       }
     }
     tc::tc_fence_before();   // the D1 reads are ordered before the next barrier (the issuer reuses D1 two layers on)
@@ -621,8 +686,8 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
       if (kind == K_BWD2 || kind == K_BWD1) {
         // a stashed evaluation leaves A_4 in tile 1 (ping-pong, mlp_h.cuh): tile 1 is the activation tile of
         // the backward evaluation, tile 0 its gradient tile
-        bwd_eval_h(ctl, T.iss, T, tG, tA, D, stash_a, stash_s, xs, ys, zs, dphase, wphase, aphase, acc_head,
-                   acc_bias);
+        bwd_eval_h<0>(ctl, T.iss, T, tG, tA, D, stash_a, stash_s, xs, ys, zs, dphase, wphase, aphase, acc_head,
+                      acc_bias);
       } else {
         float* wout = at_mid ? &T.w1[0][0] : &T.w0[0][0];
         const bool st = (kind == K_REV_B || kind == K_REV_A);
@@ -729,6 +794,274 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
     atomicAdd(reinterpret_cast<unsigned long long*>(B.counters + 10), n_done);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// PDE loss of the velocity field on the tensor cores (NVFi.get_vel_loss, models/nvfi.py:69-84; math and
+// the FP32 SIMT twin: pde.cu).  A tile = 24 points x 5 forward-mode rows (value, d/dx, d/dy, d/dz, d/dt)
+// = 120 of the 128 rows; per tile: the stashed forward-mode evaluation (vel_net_tile_h<JVP>), the
+// per-point residuals and output adjoints (one thread per point), the reverse pass (bwd_eval_h<JVP>).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPdePts = 24;
+constexpr size_t kWsStashS2 = kWsStashS + th::kStashSFloats * sizeof(float);
+static_assert(kWsStashS2 + th::kStashSFloats * sizeof(float) <= (size_t)WS_CTA_F * sizeof(float),
+              "per-CTA workspace of k_pde_jac_h exceeds WS_CTA_F");
+
+__global__ void __launch_bounds__(th::kLaunchThreads, 1)
+    k_pde_jac_h(const __grid_constant__ NvfiField F, const float* __restrict__ xyzt, const float* __restrict__ va,
+                long long n_total, float c_div, float c_tr, int want_grad, float* __restrict__ g_acc_out,
+                double* __restrict__ loss_sums, const NvfiRenderGrads D, int* counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* p = smem_raw;
+  {
+    const uint32_t a = tc::smem_u32(p);
+    p += (1024u - (a & 1023u)) & 1023u;
+  }
+  const uint32_t tA = tc::smem_u32(p);
+  const uint32_t tG = tA + th::kTileBytes;
+  const uint32_t ring = tG + th::kTileBytes;
+  th::Ctl1& ctl = *reinterpret_cast<th::Ctl1*>(p + 2 * th::kTileBytes + kStages * th::kStageBytes);
+  BwdTile& T = *reinterpret_cast<BwdTile*>(reinterpret_cast<unsigned char*>(&ctl) + ((sizeof(th::Ctl1) + 127) & ~(size_t)127));
+  unsigned char* ws = reinterpret_cast<unsigned char*>(D.workspace) + (size_t)blockIdx.x * WS_CTA_F * sizeof(float);
+  unsigned char* stash_a = ws + kWsStashA;
+  float* stash_s = reinterpret_cast<float*>(ws + kWsStashS);
+  float* stash_s2 = reinterpret_cast<float*>(ws + kWsStashS2);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  th::setup(ctl, F.vel_net, nullptr, kTmemCols);
+  if (tid == 0) {
+    ctl.prog[0] = th::SEG_FWD0;
+    ctl.prog[1] = th::SEG_BWD0;
+    ctl.prog_len = want_grad ? 2u : 1u;
+    T.gmax = 0u;
+    T.gmax_l[0] = T.gmax_l[1] = 0u;
+  }
+  __syncthreads();
+  if (warp == th::kIssuerWarp) T.iss.init(ctl, ring, kStages);
+  __syncthreads();
+  uint32_t dphase = 0, kphase = 0, wphase = 0, aphase = 0;
+  float acc_head[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, acc_bias[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const long long n_tiles = (n_total + kPdePts - 1) / kPdePts;
+  double s_div = 0.0, s_tr = 0.0;
+  // row m = 32 q + lane: point 6 q + lane / 5 of the tile, row type lane % 5 (lanes 30, 31 dead)
+  const int jt = (lane < 30) ? lane % 5 : 5;
+  const int pt = (tid >> 5) * 6 + lane / 5;
+
+  for (;;) {
+    if (tid == 0) T.batch = atomicAdd(counter, 1);
+    __syncthreads();
+    const long long tile = T.batch;
+    __syncthreads();
+    if (tile >= n_tiles) break;
+    const long long p0 = tile * kPdePts;
+    if (tid < NVFI_TM) {
+      const bool live = jt < 5 && p0 + pt < n_total;
+      const float* q = xyzt + (p0 + pt) * 4;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) T.x0[a][tid] = live ? __ldg(q + a) : 0.f;
+      T.tvec[tid] = live ? __ldg(q + 3) : 0.f;
+    }
+    __syncthreads();
+    th::vel_net_tile_h<ACT_SILU, false, 1>(ctl, T.iss, 0, &T.w0[0][0], T.x0[0], T.x0[1], T.x0[2], T.tvec, tA, dphase,
+                                           kphase, tG, stash_a, stash_s, stash_s2);
+    // ---- per point: v, J_v, residuals, output adjoints (models/nvfi.py:69-84; same arithmetic as k_pde_jac)
+    if (tid < NVFI_TM) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) T.gout[i][tid] = 0.f;
+    }
+    __syncthreads();
+    if (tid < NVFI_TM && jt == 0 && p0 + pt < n_total) {
+      const int m0 = tid;
+      const float x = T.x0[0][m0], y = T.x0[1][m0], z = T.x0[2][m0];
+      float w[6], dw[4][6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        w[i] = T.w0[i][m0];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dw[k][i] = T.w0[i][m0 + 1 + k];
+      }
+      float v[3], J[3][4];
+      basis_velocity(w, x, y, z, v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float cc[3];
+        basis_velocity(dw[k], x, y, z, cc);
+        J[0][k] = cc[0];
+        J[1][k] = cc[1];
+        J[2][k] = cc[2];
+      }
+      // explicit dependence of the basis on the position (models/velocity_field.py:77-98)
+      J[0][1] += w[5];
+      J[0][2] -= w[4];
+      J[1][0] -= w[5];
+      J[1][2] += w[3];
+      J[2][0] += w[4];
+      J[2][1] -= w[3];
+      const float div = J[0][0] + J[1][1] + J[2][2];
+      float tr[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        tr[i] = J[i][0] * v[0] + J[i][1] * v[1] + J[i][2] * v[2] + J[i][3] - __ldg(va + (p0 + pt) * 6 + 3 + i);
+      s_div += (double)div * div;
+      s_tr += (double)tr[0] * tr[0] + (double)tr[1] * tr[1] + (double)tr[2] * tr[2];
+      if (want_grad) {
+        const float gdiv = 2.f * c_div * div;
+        float gtr[3], gJ[3][4], gv[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) gtr[i] = 2.f * c_tr * tr[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            gJ[i][k] = gtr[i] * v[k] + ((i == k) ? gdiv : 0.f);
+            gv[k] += gtr[i] * J[i][k];
+          }
+          gJ[i][3] = gtr[i];
+          g_acc_out[(p0 + pt) * 3 + i] = -gtr[i];
+        }
+        float gw[6], gxe[3];
+        basis_bwd(w, x, y, z, gv, gw, gxe);   // gw = B^T gv (the position part gxe is not needed)
+        gw[5] += gJ[0][1] - gJ[1][0];
+        gw[4] += gJ[2][0] - gJ[0][2];
+        gw[3] += gJ[1][2] - gJ[2][1];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) T.gout[i][m0] = gw[i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float gc[3] = {gJ[0][k], gJ[1][k], gJ[2][k]};
+          float gd[6];
+          basis_bwd(w, x, y, z, gc, gd, gxe);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) T.gout[i][m0 + 1 + k] = gd[i];
+        }
+      }
+    }
+    __syncthreads();
+    if (want_grad) {
+      bwd_eval_h<1>(ctl, T.iss, T, tG, tA, D, stash_a, stash_s, T.x0[0], T.x0[1], T.x0[2], dphase, wphase, aphase,
+                    acc_head, acc_bias, stash_s2);
+      __syncthreads();
+    }
+  }
+  if (want_grad) {
+    if (tid < NVFI_TM) {
+#pragma unroll
+      for (int n2 = 0; n2 < 6; ++n2) red_add(D.g_vel_w[5] + tid * 8 + n2, acc_head[n2]);
+    }
+    if (tid < NT) {
+      const int col = 32 * (lane >> 3) + 8 * (warp >> 2) + (lane & 7);
+#pragma unroll
+      for (int l = 0; l < 5; ++l) red_add(D.g_vel_b[l] + col, acc_bias[l]);
+    }
+    if (warp < 6) {
+      const float s5 = warp_sum(acc_bias[5]);
+      if (lane == 0) red_add(D.g_vel_b[5] + warp, s5);
+    }
+  }
+  // ---- loss sums: warp shuffles, then one FP64 atomic per warp that has points
+  {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s_div += __shfl_xor_sync(0xffffffffu, s_div, o);
+      s_tr += __shfl_xor_sync(0xffffffffu, s_tr, o);
+    }
+    if (lane == 0 && warp < NVFI_TM / 32) {
+      atomicAdd(loss_sums, s_div);
+      atomicAdd(loss_sums + 1, s_tr);
+    }
+  }
+  if (warp == th::kIssuerWarp && tc::elect_one()) th::bulk_wait0();
+  th::teardown(ctl, T.iss, kTmemCols);
+}
+
+
+// Backward of the ReLU twin net (a_weight_net) for per-point upstream gradients ga (n, 3) of the
+// acceleration a = basis_acceleration(net(enc(q)), x) (models/velocity_field.py:69-75), on the tensor
+// cores: a stashed forward evaluation and the reverse pass of 128 points per tile (the FP32 SIMT twin is
+// k_accnet_bwd in pde.cu).  D.g_vel_w / g_vel_b point at the a_weight_net accumulators.
+__global__ void __launch_bounds__(th::kLaunchThreads, 1)
+    k_accnet_bwd_h(const __grid_constant__ NvfiField F, const float* __restrict__ xyzt, const float* __restrict__ ga,
+                   long long n_total, const NvfiRenderGrads D, int* counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* p = smem_raw;
+  {
+    const uint32_t a = tc::smem_u32(p);
+    p += (1024u - (a & 1023u)) & 1023u;
+  }
+  const uint32_t tA = tc::smem_u32(p);
+  const uint32_t tG = tA + th::kTileBytes;
+  const uint32_t ring = tG + th::kTileBytes;
+  th::Ctl1& ctl = *reinterpret_cast<th::Ctl1*>(p + 2 * th::kTileBytes + kStages * th::kStageBytes);
+  BwdTile& T = *reinterpret_cast<BwdTile*>(reinterpret_cast<unsigned char*>(&ctl) + ((sizeof(th::Ctl1) + 127) & ~(size_t)127));
+  unsigned char* ws = reinterpret_cast<unsigned char*>(D.workspace) + (size_t)blockIdx.x * WS_CTA_F * sizeof(float);
+  unsigned char* stash_a = ws + kWsStashA;
+  float* stash_s = reinterpret_cast<float*>(ws + kWsStashS);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  th::setup(ctl, F.acc_net, nullptr, kTmemCols);
+  if (tid == 0) {
+    ctl.prog[0] = th::SEG_FWD0;
+    ctl.prog[1] = th::SEG_BWD0;
+    ctl.prog_len = 2u;
+    T.gmax = 0u;
+  }
+  __syncthreads();
+  if (warp == th::kIssuerWarp) T.iss.init(ctl, ring, kStages);
+  __syncthreads();
+  uint32_t dphase = 0, kphase = 0, wphase = 0, aphase = 0;
+  float acc_head[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, acc_bias[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const long long n_tiles = (n_total + NVFI_TM - 1) / NVFI_TM;
+  for (;;) {
+    if (tid == 0) T.batch = atomicAdd(counter, 1);
+    __syncthreads();
+    const long long tile = T.batch;
+    __syncthreads();
+    if (tile >= n_tiles) break;
+    const long long i0 = tile * NVFI_TM;
+    if (tid < NVFI_TM) {
+      const bool live = i0 + tid < n_total;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) T.x0[a][tid] = live ? __ldg(xyzt + (i0 + tid) * 4 + a) : 0.f;
+      T.tvec[tid] = live ? __ldg(xyzt + (i0 + tid) * 4 + 3) : 0.f;
+    }
+    __syncthreads();
+    th::vel_net_tile_h<ACT_RELU, false>(ctl, T.iss, 0, &T.w0[0][0], T.x0[0], T.x0[1], T.x0[2], T.tvec, tA, dphase,
+                                        kphase, tG, stash_a, stash_s);
+    if (tid < NVFI_TM) {
+      const int m = tid;
+      float g[3] = {0.f, 0.f, 0.f};
+      if (i0 + m < n_total) {
+        g[0] = __ldg(ga + (i0 + m) * 3);
+        g[1] = __ldg(ga + (i0 + m) * 3 + 1);
+        g[2] = __ldg(ga + (i0 + m) * 3 + 2);
+      }
+      const float x = T.x0[0][m], y = T.x0[1][m], z = T.x0[2][m];
+      T.gout[0][m] = g[0];
+      T.gout[1][m] = g[1];
+      T.gout[2][m] = g[2];
+      T.gout[3][m] = -y * g[1] - z * g[2];
+      T.gout[4][m] = -x * g[0] - z * g[2];
+      T.gout[5][m] = -x * g[0] - y * g[1];
+    }
+    __syncthreads();
+    bwd_eval_h<0>(ctl, T.iss, T, tG, tA, D, stash_a, stash_s, T.x0[0], T.x0[1], T.x0[2], dphase, wphase, aphase,
+                  acc_head, acc_bias);
+    __syncthreads();
+  }
+  if (tid < NVFI_TM) {
+#pragma unroll
+    for (int n2 = 0; n2 < 6; ++n2) red_add(D.g_vel_w[5] + tid * 8 + n2, acc_head[n2]);
+  }
+  if (tid < NT) {
+    const int col = 32 * (lane >> 3) + 8 * (warp >> 2) + (lane & 7);
+#pragma unroll
+    for (int l = 0; l < 5; ++l) red_add(D.g_vel_b[l] + col, acc_bias[l]);
+  }
+  if (warp < 6) {
+    const float s5 = warp_sum(acc_bias[5]);
+    if (lane == 0) red_add(D.g_vel_b[5] + warp, s5);
+  }
+  if (warp == th::kIssuerWarp && tc::elect_one()) th::bulk_wait0();
+  th::teardown(ctl, T.iss, kTmemCols);
+}
+
 }  // namespace thb
 }  // namespace nvfi
 
@@ -765,5 +1098,59 @@ extern "C" int nvfi_launch_advect_bwd_h(const NvfiField* F, const NvfiRenderArgs
   const int grid = n_batches < sms ? n_batches : sms;
   NVFI_LAUNCH(thb::k_advect_bwd_h, grid, th::kLaunchThreads, smem, st, *F, *A, *B, *D, S, total, n_batches, subs);
   NVFI_CUDA_OK(cudaGetLastError());
+  return (int)cudaGetLastError();
+}
+
+// The forward-mode Jacobian + reverse pass of nvfi_pde_loss on the tensor cores (pde.cu dispatches here
+// for NVFI_MLP_F16X3): gradients are added straight into the packed accumulators of `G`.
+extern "C" int nvfi_launch_pde_jac_h(const NvfiField* F, const float* xyzt, const float* va, long long n,
+                                     float c_div, float c_tr, int want_grad, const NvfiPdeGrads* G,
+                                     double* loss_sums, int* counter, int sms, cudaStream_t st) {
+  for (int l = 0; l < NVFI_VEL_LAYERS; ++l)
+    if (!F->vel_net[l].himg || !F->vel_net[l].himgT) return NVFI_EINVAL;
+  if (F->vel_net[5].n_pad != 8) return NVFI_EUNSUPPORTED;
+  NvfiRenderGrads D;
+  memset(&D, 0, sizeof(D));
+  for (int l = 0; l < NVFI_VEL_LAYERS; ++l) {
+    D.g_vel_w[l] = G->g_vel_w[l];
+    D.g_vel_b[l] = G->g_vel_b[l];
+  }
+  D.workspace = G->workspace;
+  D.workspace_bytes = G->workspace_bytes;
+  const size_t smem = 1024 + 2 * (size_t)th::kTileBytes + (size_t)thb::kStages * th::kStageBytes +
+                      ((sizeof(th::Ctl1) + 127) & ~(size_t)127) + sizeof(thb::BwdTile);
+  {
+    const int rc = ensure_smem<thb::k_pde_jac_h>(smem);
+    if (rc != NVFI_OK) return rc;
+  }
+  const long long n_tiles = (n + thb::kPdePts - 1) / thb::kPdePts;
+  const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+  NVFI_LAUNCH(thb::k_pde_jac_h, grid, th::kLaunchThreads, smem, st, *F, xyzt, va, n, c_div, c_tr, want_grad,
+              G->g_acc_pts, loss_sums, D, counter);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int nvfi_launch_accnet_bwd_h(const NvfiField* F, const float* xyzt, const float* ga, long long n,
+                                        const NvfiPdeGrads* G, int* counter, int sms, cudaStream_t st) {
+  for (int l = 0; l < NVFI_VEL_LAYERS; ++l)
+    if (!F->acc_net[l].himg || !F->acc_net[l].himgT) return NVFI_EINVAL;
+  if (F->acc_net[5].n_pad != 8) return NVFI_EUNSUPPORTED;
+  NvfiRenderGrads D;
+  memset(&D, 0, sizeof(D));
+  for (int l = 0; l < NVFI_VEL_LAYERS; ++l) {
+    D.g_vel_w[l] = G->g_acc_w[l];
+    D.g_vel_b[l] = G->g_acc_b[l];
+  }
+  D.workspace = G->workspace;
+  D.workspace_bytes = G->workspace_bytes;
+  const size_t smem = 1024 + 2 * (size_t)th::kTileBytes + (size_t)thb::kStages * th::kStageBytes +
+                      ((sizeof(th::Ctl1) + 127) & ~(size_t)127) + sizeof(thb::BwdTile);
+  {
+    const int rc = ensure_smem<thb::k_accnet_bwd_h>(smem);
+    if (rc != NVFI_OK) return rc;
+  }
+  const long long n_tiles = (n + NVFI_TM - 1) / NVFI_TM;
+  const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+  NVFI_LAUNCH(thb::k_accnet_bwd_h, grid, th::kLaunchThreads, smem, st, *F, xyzt, ga, n, *(&D), counter);
   return (int)cudaGetLastError();
 }

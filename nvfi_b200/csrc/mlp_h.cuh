@@ -391,12 +391,19 @@ constexpr size_t kStashSFloats = 5 * (size_t)NVFI_TM * NVFI_TM;
 // backward kernel) the layers ping-pong instead — the encoding and A_1, A_3 in tile 0; A_0, A_2, A_4 in
 // tile 1 — so that the bulk copy of A_l to the stash has a whole layer to read its tile before the tile
 // is overwritten.  Whole CTA (2 block barriers).
-template <int ACT, bool TS, class C>
+//
+// JVP = 1 (the PDE loss, k_pde_jac_h): forward-mode rows.  The 32 rows of a TMEM lane quadrant hold 6
+// points x 5 rows — lane 5 p + j: j = 0 the value row, j = 1..4 the tangent d/d(x, y, z, t) — and 2 dead
+// lanes.  The linear layers are unchanged (tangent rows simply carry no bias); the activation couples the
+// rows of a point, a_j = silu'(h_0) h_j, through one warp shuffle per element.  The stash then holds
+// S = silu'(h_0) for all 5 rows and S2 = silu''(h_0) h_j for the tangent rows (stash_s2), which is all the
+// reverse pass needs: g_h0 = g_a0 S + sum_j g_aj S2_j, g_hj = g_aj S.
+template <int ACT, bool TS, int JVP = 0, class C>
 __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, const float* xs,
                                const float* ys, const float* zs, const float* ts, uint32_t tile_u32,
                                uint32_t& dphase, uint32_t& kphase, uint32_t tile1_u32 = 0u,
                                unsigned char* __restrict__ stash_a = nullptr,
-                               float* __restrict__ stash_s = nullptr) {
+                               float* __restrict__ stash_s = nullptr, float* __restrict__ stash_s2 = nullptr) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool stash = stash_a != nullptr;
   if (tile1_u32 == 0u) tile1_u32 = tile_u32;
@@ -449,6 +456,9 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
   const uint32_t row_off = (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);
   const uint32_t row_u32 = tile_u32 + row_off;
   const uint32_t x7 = (uint32_t)(m & 7);
+  // JVP: row type of this lane (0 value, 1..4 tangent, 5 dead) and the lane of its point's value row
+  const int jt = JVP ? (lane < 30 ? lane % 5 : 5) : 0;
+  const int jsrc = JVP ? (lane < 30 ? lane - jt : lane) : lane;
 
   // ---- PositionEncoder(3) of (x, y, z, t): 28 values + 4 zeros into columns [0, 32):
   // [q | sin q | cos q | sin 2q | cos 2q | sin 4q | cos 4q | 0], 8 columns per warp slot
@@ -464,6 +474,11 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
       tc::sincos_bounded(p[i] * fb, sb, cb);
       v[i] = (h == 0) ? p[i] : ca;
       v[4 + i] = (h == 3) ? 0.f : sb;
+      if (JVP && jt != 0) {   // tangent row: d/dq_i of the same entries for i = jt - 1, zero elsewhere
+        const bool mine = (i == jt - 1);
+        v[i] = mine ? ((h == 0) ? 1.f : -fa * sa) : 0.f;
+        v[4 + i] = (mine && h != 3) ? fb * cb : 0.f;
+      }
     }
     uint4 hi, lo;
     split8(v, hi, lo);
@@ -504,8 +519,31 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
       const float4 b1 = *reinterpret_cast<const float4*>(&c.bias[which][l][col + 4]);
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       float av[8], sv[8];
+      if (JVP) {
+        float s2v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) av[i] = act_h<ACT>(__uint_as_float(raw[g][i]) + bb[i], sv[i]);
+        for (int i = 0; i < 8; ++i) {
+          const float own = __uint_as_float(raw[g][i]);
+          const float hv = __shfl_sync(0xffffffffu, own, jsrc) + bb[i];   // pre-activation of the value row
+          float e, r;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(hv * -1.4426950408889634f));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+          const float a = hv * r;
+          const float d1 = fmaf(a, 1.f - r, r);                                   // silu'
+          const float d2 = r * (1.f - r) * fmaf(hv, 1.f - 2.f * r, 2.f);          // silu''
+          av[i] = (jt == 0) ? a : ((jt < 5) ? d1 * own : 0.f);
+          sv[i] = (jt < 5) ? d1 : 0.f;
+          s2v[i] = (jt >= 1 && jt < 5) ? d2 * own : 0.f;
+        }
+        if (stash) {
+          float4* sp2 = reinterpret_cast<float4*>(stash_s2) + ((size_t)l * 32 + (col >> 2)) * NVFI_TM + m;
+          __stcg(sp2, make_float4(s2v[0], s2v[1], s2v[2], s2v[3]));
+          __stcg(sp2 + NVFI_TM, make_float4(s2v[4], s2v[5], s2v[6], s2v[7]));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) av[i] = act_h<ACT>(__uint_as_float(raw[g][i]) + bb[i], sv[i]);
+      }
       if (stash) {   // quads of units: a warp stores 512 contiguous bytes per quad
         float4* sp = reinterpret_cast<float4*>(stash_s) + ((size_t)l * 32 + (col >> 2)) * NVFI_TM + m;
         __stcg(sp, make_float4(sv[0], sv[1], sv[2], sv[3]));
@@ -543,7 +581,7 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
     tc::tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 6; ++i)
-      outS[i * NVFI_TM + m] = __uint_as_float(raw[i]) + c.bias[which][NVFI_VEL_LAYERS - 1][i];
+      outS[i * NVFI_TM + m] = __uint_as_float(raw[i]) + ((JVP && jt != 0) ? 0.f : c.bias[which][NVFI_VEL_LAYERS - 1][i]);
   }
   tc::tc_fence_before();
   __syncthreads();   // (2)

@@ -50,21 +50,37 @@ class _PdeFn(torch.autograd.Function):
         va = engine.velocity(b, xyzt, True)
         sums = torch.zeros(2, device=dev, dtype=torch.float64)
         g = L.NvfiPdeGrads()
-        keep = []
-        gw = {"vel": [], "acc": []}
-        gb = {"vel": [], "acc": []}
+        nets = (("vel", b.vel, g.g_vel_w, g.g_vel_b), ("acc", b.acc, g.g_acc_w, g.g_acc_b))
+        outs = {}
         if want_grad:
-            for name, packed, dst_w, dst_b in (("vel", b.vel, g.g_vel_w, g.g_vel_b),
-                                               ("acc", b.acc, g.g_acc_w, g.g_acc_b)):
+            # ONE zero-filled buffer for the 24 packed accumulators, ONE for the gradients in nn.Linear layout
+            al = lambda x: (x + 31) // 32 * 32
+            sizes = []
+            for name, packed, _, _ in nets:
                 for j in range(L.VEL_LAYERS):
-                    w_ = torch.zeros_like(packed[j].wt)
-                    b_ = torch.zeros_like(packed[j].bias)
-                    gw[name].append(w_)
-                    gb[name].append(b_)
-                    dst_w[j], dst_b[j] = w_.data_ptr(), b_.data_ptr()
+                    sizes.append((packed[j].wt.numel(), (packed[j].out_dim, packed[j].in_dim)))
+                    sizes.append((packed[j].bias.numel(), (packed[j].out_dim,)))
+            import math
+            acc = torch.zeros(sum(al(n_) for n_, _ in sizes), **f32)
+            outbuf = torch.empty(sum(al(math.prod(sh)) for _, sh in sizes), **f32)
+            P = L.NvfiPdeParamGrads()
+            po = oo = 0
+            k = 0
+            for name, packed, dst_w, dst_b in nets:
+                pw, pb = (P.vel_w, P.vel_b) if name == "vel" else (P.acc_w, P.acc_b)
+                outs[name] = []
+                for j in range(L.VEL_LAYERS):
+                    for dst, pdst in ((dst_w, pw), (dst_b, pb)):
+                        n_, sh = sizes[k]
+                        k += 1
+                        dst[j] = acc[po:po + n_].data_ptr()
+                        o_ = outbuf[oo:oo + math.prod(sh)].view(sh)
+                        pdst[j] = o_.data_ptr()
+                        outs[name].append(o_)
+                        po += al(n_)
+                        oo += al(math.prod(sh))
             ga = torch.empty(n, 3, **f32)
             g.g_acc_pts = ga.data_ptr()
-            keep.append(ga)
         ws_bytes = int(lib.nvfi_backward_workspace_bytes())
         ws = torch.empty(ws_bytes // 4, **f32)
         g.workspace, g.workspace_bytes = ws.data_ptr(), ws_bytes
@@ -75,10 +91,8 @@ class _PdeFn(torch.autograd.Function):
         loss = (5.0 * sums[0] / n + 0.1 * sums[1] / (3.0 * n)).to(torch.float32)
         grads: List[Optional[torch.Tensor]] = []
         if want_grad:
-            for name, packed in (("vel", b.vel), ("acc", b.acc)):
-                for j in range(L.VEL_LAYERS):
-                    w_, b_ = packed[j].unpack_grad(gw[name][j], gb[name][j], True)
-                    grads += [w_, b_]
+            L.check(lib.nvfi_unpack_pde_grads(C.byref(s), C.byref(g), C.byref(P), engine._stream()), "unpack_pde_grads")
+            grads = outs["vel"] + outs["acc"]
         ctx.grads = grads
         ctx.needs = [p.requires_grad for p in params]
         return loss
