@@ -75,6 +75,7 @@ struct UnpackJob {
   float* w;
   float* b;
   int out_dim, in_dim, n_pad;
+  int v4;   // packed layout [k / 4][n][k % 4] (grad_layout_v4) instead of [k][n]
 };
 struct UnpackBatch {
   UnpackJob job[12];
@@ -85,7 +86,7 @@ __global__ void k_unpack_linear_batch(const __grid_constant__ UnpackBatch ub) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < J.out_dim * J.in_dim) {
     const int n = i / J.in_dim, k = i - n * J.in_dim;
-    J.w[i] = J.wt[k * J.n_pad + n];
+    J.w[i] = J.v4 ? J.wt[((k >> 2) * J.n_pad + n) * 4 + (k & 3)] : J.wt[k * J.n_pad + n];
   }
   if (J.b && J.bias_in && i < J.out_dim) J.b[i] = J.bias_in[i];
 }
@@ -250,16 +251,19 @@ extern "C" int nvfi_unpack_render_grads(const NvfiField* F, const NvfiRenderGrad
   UnpackBatch ub;
   memset(&ub, 0, sizeof(ub));
   int nl = 0, max_n = 0;
-  auto add = [&](const NvfiLinear& L, const float* wt, const float* bi, float* w, float* b) {
+  auto add = [&](const NvfiLinear& L, const float* wt, const float* bi, float* w, float* b, int v4 = 0) {
     if (!wt || !w) return;
-    ub.job[nl++] = UnpackJob{wt, bi, w, b, L.out_dim, L.in_dim, L.n_pad};
+    ub.job[nl++] = UnpackJob{wt, bi, w, b, L.out_dim, L.in_dim, L.n_pad, v4};
     if (L.out_dim * L.in_dim > max_n) max_n = L.out_dim * L.in_dim;
   };
   add(F->basis_mat, D->g_basis_mat, nullptr, P->basis_mat, nullptr);
   if (F->shading_mode == NVFI_SHADING_MLP_PE)
     for (int i = 0; i < 3; ++i) add(F->render_mlp[i], D->g_render_w[i], D->g_render_b[i], P->render_w[i], P->render_b[i]);
-  if (F->use_vel)
-    for (int l = 0; l < NVFI_VEL_LAYERS; ++l) add(F->vel_net[l], D->g_vel_w[l], D->g_vel_b[l], P->vel_w[l], P->vel_b[l]);
+  if (F->use_vel) {
+    const bool v4 = grad_layout_v4(F, F->vel_net);
+    for (int l = 0; l < NVFI_VEL_LAYERS; ++l)
+      add(F->vel_net[l], D->g_vel_w[l], D->g_vel_b[l], P->vel_w[l], P->vel_b[l], (v4 && l < NVFI_VEL_LAYERS - 1) ? 1 : 0);
+  }
   if (nl > 0) {
     dim3 grid((unsigned)((max_n + 255) / 256), 12);
     NVFI_LAUNCH(k_unpack_linear_batch, grid, 256, 0, st, ub);
@@ -274,6 +278,7 @@ extern "C" int nvfi_unpack_pde_grads(const NvfiField* F, const NvfiPdeGrads* G, 
   UnpackBatch ub;
   memset(&ub, 0, sizeof(ub));
   int nl = 0, max_n = 0;
+  const int v4[2] = {grad_layout_v4(F, F->vel_net) ? 1 : 0, grad_layout_v4(F, F->acc_net) ? 1 : 0};
   for (int l = 0; l < NVFI_VEL_LAYERS; ++l) {
     const struct {
       const NvfiLinear& L;
@@ -285,7 +290,8 @@ extern "C" int nvfi_unpack_pde_grads(const NvfiField* F, const NvfiPdeGrads* G, 
               {F->acc_net[l], G->g_acc_w[l], G->g_acc_b[l], P->acc_w[l], P->acc_b[l]}};
     for (int j = 0; j < 2; ++j) {
       if (!e[j].wt || !e[j].w) continue;
-      ub.job[nl++] = UnpackJob{e[j].wt, e[j].bi, e[j].w, e[j].b, e[j].L.out_dim, e[j].L.in_dim, e[j].L.n_pad};
+      ub.job[nl++] = UnpackJob{e[j].wt, e[j].bi, e[j].w, e[j].b, e[j].L.out_dim, e[j].L.in_dim, e[j].L.n_pad,
+                               (v4[j] && l < NVFI_VEL_LAYERS - 1) ? 1 : 0};
       if (e[j].L.out_dim * e[j].L.in_dim > max_n) max_n = e[j].L.out_dim * e[j].L.in_dim;
     }
   }

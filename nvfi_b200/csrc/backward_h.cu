@@ -479,14 +479,17 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
     // ---- D1[n][k] (this thread: n = m, k = 32 h + i) is added to the packed gradient [k][n]; the flush
     //      overlaps the next layer's MMAs (D1 ping-pongs in tensor memory)
     if (L > 0 || h == 0) {
-      // coalesced fire-and-forget reductions: one 128-byte line of the packed gradient per warp instruction
-      float* pp = D.g_vel_w[L] + (size_t)(h * 32) * NVFI_TM + m;
+      // coalesced fire-and-forget VECTOR reductions into the [k / 4][n][k % 4] gradient image
+      // (grad_layout_v4): 4 consecutive k per thread and instruction, 512 contiguous bytes per warp
+      float* pp = D.g_vel_w[L] + ((size_t)(h * 8) * NVFI_TM + m) * 4;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         float dv[16];
         tc::tmem_ld16(tb + lane_base + kColD1 + 128u * (uint32_t)(L & 1) + (uint32_t)(h * 32 + half * 16), dv);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) red_add(pp + (size_t)(half * 16 + i) * NVFI_TM, dv[i] * inv_L);
+        for (int q4 = 0; q4 < 4; ++q4)
+          red_add_v4(pp + (size_t)(half * 4 + q4) * NVFI_TM * 4,
+                     make_float4(dv[4 * q4] * inv_L, dv[4 * q4 + 1] * inv_L, dv[4 * q4 + 2] * inv_L, dv[4 * q4 + 3] * inv_L));
       }
     }
     tc::tc_fence_before();   // the D1 reads are ordered before the next barrier (the issuer reuses D1 two layers on)

@@ -47,6 +47,17 @@ inline int mlp_mode_of(const NvfiField* F) {
   return (m < NVFI_MLP_FP32_SIMT || m > NVFI_MLP_F16X3) ? NVFI_MLP_F16X3 : m;
 }
 
+// The FP16-split tensor-core kernels (backward_h.cu) accumulate the weight gradients of the hidden layers
+// in the layout [k / 4][n][k % 4] (a thread adds 4 consecutive k of its unit n with ONE vector reduction,
+// a warp 512 contiguous bytes) instead of the [k][n] of NvfiLinear.wt; they run when the call selects
+// NVFI_MLP_F16X3 and the net carries both FP16 images.  The unpack entry points ask the same question.
+inline bool grad_layout_v4(const NvfiField* F, const NvfiLinear* net) {
+  if (mlp_mode_of(F) != NVFI_MLP_F16X3) return false;
+  for (int l = 0; l < NVFI_VEL_LAYERS; ++l)
+    if (!net[l].himg || !net[l].himgT) return false;
+  return true;
+}
+
 constexpr int kMaxDevices = 64;
 inline int current_device() {
   int dev = 0;

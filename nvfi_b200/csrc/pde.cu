@@ -474,8 +474,7 @@ extern "C" int nvfi_pde_loss(const NvfiField* F, const float* xyzt, const float*
   // NVFi.get_vel_loss: 5 * mean(div^2) + 0.1 * mean(transport^2) over (n) and (n, 3) entries
   const float c_div = (float)(5.0 / (double)n), c_tr = (float)(0.1 / (3.0 * (double)n));
   const size_t tile_smem = (size_t)(2 * TILE_F + 2 * NVFI_KC * 128) * sizeof(float);
-  bool h16 = mlp_mode_of(F) == NVFI_MLP_F16X3;
-  for (int l = 0; l < NVFI_VEL_LAYERS && h16; ++l) h16 = F->vel_net[l].himg && F->vel_net[l].himgT;
+  const bool h16 = grad_layout_v4(F, F->vel_net);
   if (h16) {   // product path: forward-mode rows on the tensor cores (backward_h.cu: k_pde_jac_h)
     const int rc = nvfi_launch_pde_jac_h(F, xyzt, va, (long long)n, c_div, c_tr, (int)want_grad, G, loss_sums,
                                          counters, sms, st);
@@ -493,8 +492,7 @@ extern "C" int nvfi_pde_loss(const NvfiField* F, const float* xyzt, const float*
     NVFI_CUDA_OK(cudaGetLastError());
     if (want_grad) reduce_net(G->workspace, grid, G->g_vel_w, G->g_vel_b, st);
   }
-  bool h16a = want_grad && mlp_mode_of(F) == NVFI_MLP_F16X3;
-  for (int l = 0; l < NVFI_VEL_LAYERS && h16a; ++l) h16a = F->acc_net[l].himg && F->acc_net[l].himgT;
+  const bool h16a = want_grad && grad_layout_v4(F, F->acc_net);
   if (h16a) {
     const int rc = nvfi_launch_accnet_bwd_h(F, xyzt, G->g_acc_pts, (long long)n, G, counters + 1, sms, st);
     if (rc != NVFI_OK) return rc;
