@@ -24,7 +24,10 @@
 // Tried and rejected on the bench workload (all parity-green): TMA bulk reduce-add of D1 staged in T_A
 // (353 ms: the staging tile, the reduction's read and the next A_{l-2} load serialise), per-CTA private
 // partials with plain read-modify-write (291 ms: two exposed L2 round trips per layer), constant-ones
-// MMAs for the bias sums (16 tiny MMAs per layer cost ~650 cycles of tensor time).
+// MMAs for the bias sums (16 tiny MMAs per layer cost ~650 cycles of tensor time), 4 dedicated flush
+// warps that read D1 out under the next layer's epilogue (259 ms against 222: 21 warps cap the kernel at
+// 80 registers, and 4 warps push the 64 KB of reductions per layer slower than 16 do), vector reductions
+// (red.global.add.v4.f32, kept: same time — the flush is bound by RED bytes per SM, ~12 B/clk).
 //
 // FP16 range: the upstream gradient of a tile is scaled by a power of two so that its largest
 // component is in [8, 16) (12 binades of headroom for growth through the layers, 2^-29 of the tile
