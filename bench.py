@@ -385,7 +385,7 @@ def run_gpu(args):
             loss = self.loss_of(rgb, self.target_d)
             loss.backward()
             if world > 1 and collective:
-                loss = sharding.allreduce_grads(params, extras=loss.detach().reshape(1))
+                loss = sharding.allreduce_grads(params, extras=loss.detach().reshape(1), flat=engine.last_grad_flat())
             return loss
 
         def e2e(self):
@@ -399,7 +399,7 @@ def run_gpu(args):
             loss = self.loss_of(rgb, tgt)
             loss.backward()
             if world > 1:
-                loss = sharding.allreduce_grads(params, extras=loss.detach().reshape(1))
+                loss = sharding.allreduce_grads(params, extras=loss.detach().reshape(1), flat=engine.last_grad_flat())
             return float(loss.item()), rays
 
     # ---- headline: STRONG scaling, one frame per step sharded over the ranks
@@ -433,7 +433,8 @@ def run_gpu(args):
 
     # ---- the step's fixed costs beside the kernels (strong scaling exposes them): the gradient all-reduce
     if world > 1:
-        ms_ar = timed(lambda: sharding.allreduce_grads(params, extras=torch.zeros(1, device=dev)), K) / K
+        ms_ar = timed(lambda: sharding.allreduce_grads(params, extras=torch.zeros(1, device=dev),
+                                                       flat=engine.last_grad_flat()), K) / K
         ms_nocoll = timed(lambda: job.resident(collective=False), K) / K
         line["strong_breakdown"] = {"ms_step": ms_step, "ms_step_without_collective": ms_nocoll,
                                     "ms_allreduce_alone": ms_ar,

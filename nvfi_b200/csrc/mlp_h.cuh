@@ -302,7 +302,9 @@ __device__ __forceinline__ void ring_advance(Issuer& is) {
   --is.in_flight;
 }
 template <class C>
-__device__ inline void drain(C& c, Issuer& is) {
+__device__ inline void drain(C& c, Issuer& is_ref) {
+  Issuer is = is_ref;   // registers: `is_ref` may live in shared memory, where 32 lanes updating it in lock
+                        // step is a (same-value) write-write hazard for compute-sanitizer racecheck
   while (is.in_flight > 0) {
     tc::mbar_wait(&c.full[is.c_stage], is.c_round & 1);
     ring_advance(is);

@@ -479,6 +479,16 @@ def render_forward(binding: FieldBinding, rays_o: torch.Tensor, rays_d: torch.Te
     return o
 
 
+GRAD_FLAT_TAIL = 256
+# (flat buffer, floats used) of the most recent render_backward: every gradient it returned is a view of
+# this ONE buffer, so a data-parallel step can all-reduce it in place (sharding.allreduce_grads(flat=...))
+LAST_GRAD_FLAT: Optional[Tuple[torch.Tensor, int]] = None
+
+
+def last_grad_flat() -> Optional[Tuple[torch.Tensor, int]]:
+    return LAST_GRAD_FLAT
+
+
 DEBUG_KEEP: Optional[dict] = None   # tests may set this to a dict to receive backward intermediates
 LAST_BWD_COUNTERS: Optional[torch.Tensor] = None   # int32[16] of the most recent render_backward
 
@@ -526,7 +536,10 @@ def render_backward(binding: FieldBinding, out: RenderOutputs, g_rgb, g_depth, g
             sizes.append((pl.bias.numel(), (pl.out_dim,)))
     al = lambda x: (x + 31) // 32 * 32      # 128-byte alignment of every slice
     packed = torch.zeros(sum(al(n) for n, _ in sizes), **f32)
-    outbuf = torch.empty(sum(al(math.prod(sh)) for _, sh in sizes), **f32)
+    used = sum(al(math.prod(sh)) for _, sh in sizes)
+    # zero-filled (the alignment gaps travel through the all-reduce of sharding.allreduce_grads) with a
+    # tail for that collective's flags and extras
+    outbuf = torch.zeros(used + GRAD_FLAT_TAIL, **f32)
     pk, ov = [], []
     po = oo = 0
     for n_, sh in sizes:
@@ -571,8 +584,9 @@ def render_backward(binding: FieldBinding, out: RenderOutputs, g_rgb, g_depth, g
     L.check(lib.nvfi_render_backward(C.byref(s), C.byref(a), C.byref(b), C.byref(d), _stream()),
             "render_backward")
     L.check(lib.nvfi_unpack_render_grads(C.byref(s), C.byref(d), C.byref(P), _stream()), "unpack_render_grads")
-    global LAST_BWD_COUNTERS
+    global LAST_BWD_COUNTERS, LAST_GRAD_FLAT
     LAST_BWD_COUNTERS = out.counters
+    LAST_GRAD_FLAT = (outbuf, used)
     if DEBUG_KEEP is not None:
         DEBUG_KEEP.update(g_sigma=g_sig, g_x_adv=g_x, g_rgb_eff=g_eff, fwd=out)
     grads: List[Optional[torch.Tensor]] = [None if i is None else ov[i] for i in grads_idx]

@@ -131,8 +131,42 @@ def gather_frame_interleaved(parts: Sequence[torch.Tensor], n_rays: int, ray_chu
     return res
 
 
+def _allreduce_in_place(plist, extras, group, average, flat, ws) -> Optional[torch.Tensor]:
+    """Zero-copy variant: every existing gradient is a view of ``flat[0]`` (engine.render_backward hands out
+    views of one buffer), so that buffer — with the has-grad flags and the extras written into its tail — is
+    all-reduced in place.  Returns None when the precondition does not hold (the caller then copies)."""
+    buf, used = flat
+    n_p = len(plist)
+    n_e = extras.numel() if extras is not None else 0
+    if used + n_p + n_e > buf.numel():
+        return None
+    base = buf.untyped_storage().data_ptr()
+    lo, hi = buf.data_ptr(), buf.data_ptr() + used * 4
+    for p in plist:
+        g = p.grad
+        if g is None:
+            continue
+        if (g.dtype != torch.float32 or not g.is_contiguous() or g.untyped_storage().data_ptr() != base
+                or not (lo <= g.data_ptr() and g.data_ptr() + g.numel() * 4 <= hi)):
+            return None
+    flags = torch.tensor([0.0 if p.grad is None else 1.0 for p in plist], device=buf.device)
+    buf[used:used + n_p].copy_(flags)
+    if n_e:
+        buf[used + n_p:used + n_p + n_e].copy_(extras.reshape(-1).float())
+    view = buf[:used + n_p + n_e]
+    dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group)
+    got = buf[used:used + n_p].tolist()
+    for p, f0, f1 in zip(plist, flags.tolist(), got):
+        if f1 not in (0.0, float(ws)):
+            raise RuntimeError("nvfi_b200.sharding: a parameter has a gradient on some ranks only; "
+                               "call allreduce_grads without flat= for such steps")
+    if average:
+        buf[:used].mul_(1.0 / ws)
+    return buf[used + n_p:used + n_p + n_e].clone() if n_e else torch.zeros(0, device=buf.device)
+
+
 def allreduce_grads(params: Iterable[torch.nn.Parameter], extras: Optional[torch.Tensor] = None,
-                    group=None, average: bool = False) -> Optional[torch.Tensor]:
+                    group=None, average: bool = False, flat=None) -> Optional[torch.Tensor]:
     """Train: ONE all-reduce(sum) over [all param grads || has-grad flags || extras] in a flat FP32 buffer.
 
     ``extras`` (1-D tensor) carries scalars that must be summed across ranks as well (loss
@@ -143,13 +177,22 @@ def allreduce_grads(params: Iterable[torch.nn.Parameter], extras: Optional[torch
     0.0 on a rank with no occupied point and leaves ``a_weight_net`` without grads there, but not on
     the others); a parameter without a gradient on every rank stays None, as in the single-process
     run.  With ``average`` the gradients are divided by the world size afterwards (use it when every
-    rank's loss is already a mean over its own, equally sized block)."""
+    rank's loss is already a mean over its own, equally sized block).
+
+    ``flat`` = ``engine.last_grad_flat()``: when every gradient of the step came out of ONE
+    ``render_backward`` call they are views of one buffer, which is then reduced in place — no flattening
+    copies of the 38 MB of gradients before and after the collective (strong scaling at 8 GPUs: the
+    copies were 1.2 ms of a 50 ms step).  Falls back to the copying path when a gradient lives elsewhere."""
     rank, ws = world()
     plist = [p for p in params if p.requires_grad]
     if ws == 1:
         return extras
     if not plist and extras is None:
         return None
+    if flat is not None:
+        res = _allreduce_in_place(plist, extras, group, average, flat, ws)
+        if res is not None:
+            return res if extras is not None else None
     dev = plist[0].device if plist else extras.device
     n_p = len(plist)
     n_e = extras.numel() if extras is not None else 0

@@ -75,6 +75,22 @@ def _worker(rank, ws, port, q):
         ok_grad = ok_grad and lone.grad is not None and torch.equal(lone.grad, torch.tensor([1.0, 2.0, 3.0])) \
             and unused.grad is None
         ok_extra = abs(float(extras[0]) - float(ref)) < 1e-3 * float(ref) and int(extras[1]) == n
+        # zero-copy variant: the gradients are views of ONE buffer with a tail (engine.render_backward's layout)
+        buf = torch.zeros(64 + 32)
+        pa, pb, pn = (torch.nn.Parameter(torch.zeros(2, 3)), torch.nn.Parameter(torch.zeros(5)),
+                      torch.nn.Parameter(torch.zeros(4)))
+        pa.grad, pb.grad = buf[0:6].view(2, 3), buf[32:37]
+        pa.grad.fill_(float(rank + 1))
+        pb.grad.fill_(10.0 * (rank + 1))
+        ex = sharding.allreduce_grads([pa, pb, pn], extras=torch.tensor([float(rank)]), flat=(buf, 64))
+        ok_flat = (pa.grad.data_ptr() == buf.data_ptr() and torch.equal(pa.grad, torch.full((2, 3), 3.0))
+                   and torch.equal(pb.grad, torch.full((5,), 30.0)) and pn.grad is None and float(ex[0]) == 1.0)
+        # a gradient outside the buffer -> silent fall back to the copying path, same result
+        pc = torch.nn.Parameter(torch.zeros(3))
+        pc.grad = torch.full((3,), float(rank + 1))
+        sharding.allreduce_grads([pa, pc], flat=(buf, 64))
+        ok_flat = ok_flat and torch.equal(pc.grad, torch.full((3,), 3.0)) and torch.equal(pa.grad, torch.full((2, 3), 6.0))
+        ok_grad = ok_grad and ok_flat
         q.put((rank, ok_gather, ok_grad, ok_extra))
     finally:
         dist.destroy_process_group()
