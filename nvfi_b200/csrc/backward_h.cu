@@ -91,6 +91,7 @@ struct BwdTile {
   int batch;
   unsigned gmax;            // bits of the largest |upstream gradient| of the tile
   unsigned gmax_l[2];       // JVP: the same per layer (ping-pong)
+  unsigned gmax3[3];        // largest |G_{L-1}| recorded by layer L (slot L % 3), read by layer L - 1
   th::Issuer iss;           // weight-ring state of the issuer warp between calls
 };
 
@@ -322,6 +323,7 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
   }
   if (warp < 6 && value_row)   // db5[n] = sum_m gout[n][m]: warp n, each lane 4 samples (reduced at kernel end)
     acc_bias[5] += T.gout[warp][lane] + T.gout[warp][lane + 32] + T.gout[warp][lane + 64] + T.gout[warp][lane + 96];
+  if (tid == 0) T.gmax3[5 % 3] = 0u;   // the head layer records first; the other slots are cleared one layer ahead
   tc::tc_fence_before();
   NVFI_TLH(100, 0);
   __syncthreads();   // (A)
@@ -339,10 +341,10 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
     }
   };
   load_s(4);
-  float inv_cum = inv_scale;   // JVP: 1 / (cumulative scale of G_L), updated layer by layer
+  float inv_cum = inv_scale;   // 1 / (cumulative scale of G_L), updated layer by layer
 #pragma unroll 1
   for (int L = 5; L >= 0; --L) {
-    const float inv_L = JVP ? inv_cum : inv_scale;   // un-scaling of this layer's weight gradient
+    const float inv_L = inv_cum;   // un-scaling of this layer's weight gradient (G_L carries the cumulative scale)
     NVFI_TLH(110 + L, 0);
     tc::mbar_wait(&c.dbar, dphase & 1);   // D0 = dX(L)
     ++dphase;
@@ -358,17 +360,42 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
       for (int g = 0; g < 4; ++g) tc::tmem_ld8_nowait(dcol + 32u * g, raw[g]);
       tc::tmem_ld_wait();
       if (!JVP) {
+        // Re-scaling without a barrier: G shrinks by ~0.3 per layer and the per-sample gradients of a tile
+        // span orders of magnitude, so by the first layers most entries would sit in FP16's subnormal range
+        // (absolute resolution 2^-25 of the scaled value: the first layer's weight gradient was 7e-5 off).
+        // Every layer records the largest |G_{L-1}| of the tile (gmax3[L % 3]); the NEXT layer — one block
+        // barrier later — multiplies its result by the power of two that would have put that maximum into
+        // [8, 16).  The information is one layer stale, which the 12 binades of headroom absorb.
+        float f = 1.f;
+        if (L < 5) {
+          const unsigned bm = T.gmax3[(L + 1) % 3];
+          if (bm) {
+            unsigned ex = bm >> 23;
+            ex = ex < 30u ? 30u : (ex > 250u ? 250u : ex);
+            f = __uint_as_float((257u - ex) << 23);
+            inv_cum *= __uint_as_float((ex - 3u) << 23);
+          }
+        }
+        if (tid == 0) T.gmax3[(L + 2) % 3] = 0u;   // the slot layer L - 1 will record into
+        float mx = 0.f;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const float s8[8] = {sv[g][0].x, sv[g][0].y, sv[g][0].z, sv[g][0].w, sv[g][1].x, sv[g][1].y, sv[g][1].z, sv[g][1].w};
           float v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[g][i]) * s8[i];
+          for (int i = 0; i < 8; ++i) {
+            v[i] = __uint_as_float(raw[g][i]) * (s8[i] * f);
+            mx = fmaxf(mx, fabsf(v[i]));
+          }
           th::split8(v, ghi[g], glo[g]);
           // bias gradient of layer L - 1: column sums of G_{L-1} over the warp's 32 samples; lane j keeps
           // column 32 (j >> 3) + 8 h + (j & 7)
           const float cs = colsum8(v, lane);
           if ((lane >> 3) == g) bsum = cs;
+        }
+        {
+          const unsigned bw = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+          if (lane == 0 && bw) atomicMax(&T.gmax3[L % 3], bw);
         }
       } else {
         // forward-mode rows: the value row collects the second-order terms of its 4 tangent rows, and the
@@ -422,7 +449,7 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
           if ((lane >> 3) == g) bsum = cs;
         }
       }
-      acc_bias[L - 1] = fmaf(bsum, JVP ? inv_cum : inv_scale, acc_bias[L - 1]);
+      acc_bias[L - 1] = fmaf(bsum, inv_cum, acc_bias[L - 1]);
     } else if (!JVP && h == 0) {
       // dL/d(encoding) -> dL/d(x, y, z)  (encoder tangents)
       float ge[32];
@@ -434,7 +461,7 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
         tc::sincos_bounded(qv[i], s1, c1);
         tc::sincos_bounded(qv[i] * 2.f, s2, c2);
         tc::sincos_bounded(qv[i] * 4.f, s4, c4);
-        T.gout[i][m] = inv_scale * (ge[i] + ge[4 + i] * c1 - ge[8 + i] * s1 +
+        T.gout[i][m] = inv_cum * (ge[i] + ge[4 + i] * c1 - ge[8 + i] * s1 +
                                     2.f * (ge[12 + i] * c2 - ge[16 + i] * s2) +
                                     4.f * (ge[20 + i] * c4 - ge[24 + i] * s4));
       }
