@@ -65,6 +65,7 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColD0 = 0;              // input-gradient accumulator (forward evaluations: 0 / 128)
 constexpr uint32_t kColD1 = 256;            // weight-gradient accumulators: layer l -> 256 + 128 (l & 1)
 constexpr uint32_t kColDh = 384;            // head weight gradient (16 columns; read before layer 3 writes there)
+constexpr uint32_t kColGhi = 128, kColGlo = 192;   // G_l as the TS-form A operand of dX (two FP16 per column)
 
 // per-CTA global scratch (byte offsets)
 constexpr size_t kWsStashA = 0;
@@ -234,12 +235,12 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
         if (tc::elect_one()) {
 #pragma unroll
           for (uint32_t ks = 0; ks < 4; ++ks) {
-            const uint32_t a_h = th::desc_lo(tG + kb * th::kSlab) + ks * 2u;
-            const uint32_t a_l = th::desc_lo(tG + th::kLoOff + kb * th::kSlab) + ks * 2u;
+            // A = G_l from tensor memory (TS form: the MMAs only read the weights from shared memory)
+            const uint32_t ta = tb + (kb * 4u + ks) * 8u;
             const uint32_t b_h = th::desc_lo(st) + ks * 2u, b_l = th::desc_lo(st + nx * 128u) + ks * 2u;
-            th::mma_f16_ss(tb + kColD0, a_h, hs, b_h, hs, idx, (kb | ks) ? 1u : 0u);
-            th::mma_f16_ss(tb + kColD0, a_l, hs, b_h, hs, idx, 1u);
-            th::mma_f16_ss(tb + kColD0, a_h, hs, b_l, hs, idx, 1u);
+            th::mma_f16_ts(tb + kColD0, ta + kColGhi, b_h, hs, idx, (kb | ks) ? 1u : 0u);
+            th::mma_f16_ts(tb + kColD0, ta + kColGlo, b_h, hs, idx, 1u);
+            th::mma_f16_ts(tb + kColD0, ta + kColGhi, b_l, hs, idx, 1u);
           }
           tc::tc_commit(&c.empty[is.c_stage]);
           if (kb == 1) tc::tc_commit(&c.dbar);
@@ -388,11 +389,14 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
             mx = fmaxf(mx, fabsf(v[i]));
           }
           th::split8(v, ghi[g], glo[g]);
+          th::tmem_st4(tb + lane_base + kColGhi + (uint32_t)(16 * g + 4 * h), ghi[g]);   // A operand of dX(L - 1)
+          th::tmem_st4(tb + lane_base + kColGlo + (uint32_t)(16 * g + 4 * h), glo[g]);
           // bias gradient of layer L - 1: column sums of G_{L-1} over the warp's 32 samples; lane j keeps
           // column 32 (j >> 3) + 8 h + (j & 7)
           const float cs = colsum8(v, lane);
           if ((lane >> 3) == g) bsum = cs;
         }
+        tc::tmem_st_wait();
         {
           const unsigned bw = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
           if (lane == 0 && bw) atomicMax(&T.gmax3[L % 3], bw);
@@ -441,6 +445,8 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = vv[g][i] * f;
           th::split8(v, ghi[g], glo[g]);
+          th::tmem_st4(tb + lane_base + kColGhi + (uint32_t)(16 * g + 4 * h), ghi[g]);
+          th::tmem_st4(tb + lane_base + kColGlo + (uint32_t)(16 * g + 4 * h), glo[g]);
           if (!value_row) {   // bias gradients come from the value rows only
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = 0.f;
@@ -448,6 +454,7 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
           const float cs = colsum8(v, lane);
           if ((lane >> 3) == g) bsum = cs;
         }
+        tc::tmem_st_wait();
       }
       acc_bias[L - 1] = fmaf(bsum, inv_cum, acc_bias[L - 1]);
     } else if (!JVP && h == 0) {
@@ -724,8 +731,10 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
       } else {
         float* wout = at_mid ? &T.w1[0][0] : &T.w0[0][0];
         const bool st = (kind == K_REV_B || kind == K_REV_A);
-        th::vel_net_tile_h<ACT_SILU, false>(ctl, T.iss, 0, wout, xs, ys, zs, T.tvec, tA, dphase, kphase, st ? tG : 0u,
-                                     st ? stash_a : nullptr, st ? stash_s : nullptr);
+        // TS form (activations also in tensor memory, columns 384..511: free between backward evaluations):
+        // SS-form MMAs of this shape are bound by the shared-memory operand reads (~120 cycles against 68)
+        th::vel_net_tile_h<ACT_SILU, true>(ctl, T.iss, 0, wout, xs, ys, zs, T.tvec, tA, dphase, kphase, st ? tG : 0u,
+                                    st ? stash_a : nullptr, st ? stash_s : nullptr);
       }
       // ---- glue after the evaluation
       if (tid < NVFI_TM) {
