@@ -426,6 +426,7 @@ def run_gpu(args):
                   "[all-reduce] + loss.item(); bytes are the whole job's (all ranks)"}
     del rays_obj
 
+    sharding.check_pending()
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world), "e2e": e2e,

@@ -131,6 +131,24 @@ def gather_frame_interleaved(parts: Sequence[torch.Tensor], n_rays: int, ray_chu
     return res
 
 
+_PENDING = None      # (summed has-grad flags of the last in-place all-reduce, world size): verified lazily
+
+
+def check_pending() -> None:
+    """The in-place all-reduce requires that a parameter has a gradient on every rank or on none.  The summed
+    flags of a step are checked here — at the start of the next in-place step, or when the caller asks —
+    instead of with a device->host sync at the end of every step."""
+    global _PENDING
+    if _PENDING is None:
+        return
+    flags, ws = _PENDING
+    _PENDING = None
+    bad = [i for i, f in enumerate(flags.tolist()) if f not in (0.0, ws)]
+    if bad:
+        raise RuntimeError(f"nvfi_b200.sharding: parameters {bad} had a gradient on some ranks only in the previous "
+                           "in-place all-reduce; call allreduce_grads without flat= for such steps")
+
+
 def _allreduce_in_place(plist, extras, group, average, flat, ws) -> Optional[torch.Tensor]:
     """Zero-copy variant: every existing gradient is a view of ``flat[0]`` (engine.render_backward hands out
     views of one buffer), so that buffer — with the has-grad flags and the extras written into its tail — is
@@ -154,12 +172,10 @@ def _allreduce_in_place(plist, extras, group, average, flat, ws) -> Optional[tor
     if n_e:
         buf[used + n_p:used + n_p + n_e].copy_(extras.reshape(-1).float())
     view = buf[:used + n_p + n_e]
+    check_pending()          # the previous step's flags, one step late: no host sync inside a step
     dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group)
-    got = buf[used:used + n_p].tolist()
-    for p, f0, f1 in zip(plist, flags.tolist(), got):
-        if f1 not in (0.0, float(ws)):
-            raise RuntimeError("nvfi_b200.sharding: a parameter has a gradient on some ranks only; "
-                               "call allreduce_grads without flat= for such steps")
+    global _PENDING
+    _PENDING = (buf[used:used + n_p].clone(), float(ws))
     if average:
         buf[:used].mul_(1.0 / ws)
     return buf[used + n_p:used + n_p + n_e].clone() if n_e else torch.zeros(0, device=buf.device)

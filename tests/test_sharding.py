@@ -85,11 +85,22 @@ def _worker(rank, ws, port, q):
         ex = sharding.allreduce_grads([pa, pb, pn], extras=torch.tensor([float(rank)]), flat=(buf, 64))
         ok_flat = (pa.grad.data_ptr() == buf.data_ptr() and torch.equal(pa.grad, torch.full((2, 3), 3.0))
                    and torch.equal(pb.grad, torch.full((5,), 30.0)) and pn.grad is None and float(ex[0]) == 1.0)
+        sharding.check_pending()         # flags of the in-place step agree on both ranks
         # a gradient outside the buffer -> silent fall back to the copying path, same result
         pc = torch.nn.Parameter(torch.zeros(3))
         pc.grad = torch.full((3,), float(rank + 1))
         sharding.allreduce_grads([pa, pc], flat=(buf, 64))
         ok_flat = ok_flat and torch.equal(pc.grad, torch.full((3,), 3.0)) and torch.equal(pa.grad, torch.full((2, 3), 6.0))
+        # ... and a gradient that exists on one rank only is reported (one step late, by check_pending)
+        pd = torch.nn.Parameter(torch.zeros(4))
+        if rank == 1:
+            pd.grad = buf[40:44]
+        sharding.allreduce_grads([pa, pd], flat=(buf, 64))
+        try:
+            sharding.check_pending()
+            ok_flat = False
+        except RuntimeError:
+            pass
         ok_grad = ok_grad and ok_flat
         q.put((rank, ok_gather, ok_grad, ok_extra))
     finally:
