@@ -27,7 +27,10 @@
 // MMAs for the bias sums (16 tiny MMAs per layer cost ~650 cycles of tensor time), 4 dedicated flush
 // warps that read D1 out under the next layer's epilogue (259 ms against 222: 21 warps cap the kernel at
 // 80 registers, and 4 warps push the 64 KB of reductions per layer slower than 16 do), vector reductions
-// (red.global.add.v4.f32, kept: same time — the flush is bound by RED bytes per SM, ~12 B/clk).
+// (red.global.add.v4.f32, kept: same time — the flush is bound by RED bytes per SM, ~12 B/clk), the flush
+// of layer l + 1 interleaved, 8 columns per group, with the epilogue of layer l (249 ms: the reductions
+// stall the in-order warps just the same, and they now sit BEFORE the barrier that releases dX(l - 1)
+// instead of running under the next layer's MMAs).
 //
 // FP16 range: the upstream gradient of a tile is scaled by a power of two so that its largest
 // component is in [8, 16) (12 binades of headroom for growth through the layers, 2^-29 of the tile
