@@ -368,7 +368,11 @@ class TensorVMKeyframeTimeKplane(nn.Module):
         chunk = int(ray_chunk) if ray_chunk else max(n, 1)
         n_chunks = n // chunk + int(n % chunk > 0)
         training = self.training
-        if training and jitter is None:
+        if training and jitter is None and white_bg:
+            # one draw for all chunks: the CPU generator fills sequentially, so this IS the stream of the
+            # reference's per-chunk draws (tests/test_time_plan.py pins the equivalence) at a third of the cost
+            jitter = torch.rand(n, 1)
+        elif training and jitter is None:
             jit, bgs = [], []
             for c in range(n_chunks):
                 m = min(chunk, n - c * chunk)

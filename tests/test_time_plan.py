@@ -84,3 +84,15 @@ def test_packed_copy_cache_key_and_invalidate():
     assert not tr.stale((p,))
     engine.FieldBinding.invalidate()
     assert tr.stale((p,)) and not tr.stale((p,))
+
+
+def test_single_jitter_draw_equals_per_chunk_draws():
+    """field.render_rays draws the stratified jitter of all chunks at once when no per-chunk background
+    draw is interleaved (white background): the CPU generator's stream must not depend on the split."""
+    import torch
+    for sizes in ([2048] * 5 + [1024], [7, 9, 16, 5], [1, 1, 1, 31], [4096, 3]):
+        torch.manual_seed(3)
+        a = torch.cat([torch.rand(s, 1) for s in sizes])
+        torch.manual_seed(3)
+        b = torch.rand(sum(sizes), 1)
+        assert torch.equal(a, b), sizes
