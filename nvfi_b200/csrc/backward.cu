@@ -166,7 +166,20 @@ __global__ void __launch_bounds__(256, 3)
   for (int c = 0; c < n_it; ++c) {
     const int s = c * 32 + lane;
     const bool v = (s < S) && (B.valid[row + s] != 0);
-    unsigned m = __ballot_sync(0xffffffffu, v);
+    // Only samples with a non-zero dL/dsigma get one of the warp's 4 gather slots: behind a saturated surface
+    // the gradient is exactly zero (44 % of the valid samples of the bench frame), and such a sample would
+    // keep an 8-lane group idle for a whole round.  Its dL/dx is written here (coalesced loads of g_sigma).
+    const float gs_own = v ? D.g_sigma[row + s] : 0.f;
+    const bool p = v && gs_own != 0.f;
+    if (v && !p) {
+      const bool is_app = (D.g_rgb != nullptr) && (B.weights[row + s] > F.weight_thres);
+      if (!is_app) {   // an appearance sample keeps the gradient k_app_bwd wrote
+        D.g_x_adv[(row + s) * 3 + 0] = 0.f;
+        D.g_x_adv[(row + s) * 3 + 1] = 0.f;
+        D.g_x_adv[(row + s) * 3 + 2] = 0.f;
+      }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, p);
     while (m) {
       unsigned mm = m;
       int mine = -1;
@@ -177,11 +190,11 @@ __global__ void __launch_bounds__(256, 3)
         mm &= mm - 1;
       }
       m = mm;
+      const float gsig = __shfl_sync(0xffffffffu, gs_own, mine >= 0 ? mine : 0);
       if (mine >= 0) {
         const long long gi = row + c * 32 + mine;
         const float xt[4] = {__ldg(B.x_adv + gi * 3 + 0), __ldg(B.x_adv + gi * 3 + 1),
                              __ldg(B.x_adv + gi * 3 + 2), A.t_norm_base};
-        const float gsig = D.g_sigma[gi];
         const float sigma = B.sigma[gi];
         float feat = 0.f;
         if (F.fea2dense_act != NVFI_ACT_SOFTPLUS) feat = density_feature_group(F, xt, l8);
