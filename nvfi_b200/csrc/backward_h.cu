@@ -30,7 +30,12 @@
 // (red.global.add.v4.f32, kept: same time — the flush is bound by RED bytes per SM, ~12 B/clk), the flush
 // of layer l + 1 interleaved, 8 columns per group, with the epilogue of layer l (249 ms: the reductions
 // stall the in-order warps just the same, and they now sit BEFORE the barrier that releases dX(l - 1)
-// instead of running under the next layer's MMAs).
+// instead of running under the next layer's MMAs), the two stashed evaluations of a single-step call as the two
+// tiles of ONE paired evaluation with two stash slots (273 ms: the pair took 77 K cycles against 2 x 41 K —
+// the in-place tile images must be read out by the TMA engine before the next epilogue may overwrite them,
+// and 2 x 672 KB of stash per CTA no longer fit the L2 at all).  Timing experiments with parts switched
+// off: without the S stash stores 229 ms (L2 write bandwidth is not the limiter), without the flush's
+// reductions 210 ms (the flush costs 8 % on the critical path, not the 20 % its phase length suggests).
 //
 // FP16 range: the upstream gradient of a tile is scaled by a power of two so that its largest
 // component is in [8, 16) (12 binades of headroom for growth through the layers, 2^-29 of the tile
