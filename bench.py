@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """bench.py — rays/s of the NVFi train step (render forward + MSE + hand-written backward)
-on the BASELINE.json workload: bat.yaml, one 800x800 frame (640 000 rays) per GPU per step,
+on the BASELINE.json workload: bat.yaml, ONE 800x800 frame (640 000 rays) per step,
 192 samples/ray, final 199^3 grid, K = 16 keyframes, non-keyframe time (every valid sample is
 advected by one RK2 step = 2 velocity-MLP evaluations).
 
@@ -13,14 +13,14 @@ Prints ONE JSON line (rank 0).  Keys (see DESIGN.md "Measurement"):
                 loss.item()) with HOST ray / target buffers: H2D and D2H inside the timed region
   roofline      dominant kernel: algorithmic FLOPs (or bytes) per launch / its CUDA-event time,
                 measured live through the library's per-launch event hook (no profiler)
-  kernels       the same for every kernel of the step
-  cpu_baseline  the CPU oracle (a torch restatement of the reference algorithm) on a bounded
-                sample of the same workload, all host threads
-  --impl reference  times only that CPU leg (the reference has no native code and cannot travel
-                to the GPU box; the oracle port is pinned to it by tests/golden/*)
-Multi-GPU: weak scaling — every rank renders its own 800x800 frame (same camera = identical work
-per GPU, rank-specific jitter and target) and the ranks exchange ONE all-reduce of the flat gradient
-buffer per step.
+  kernels       the same for every kernel of the step (+ L2 figures for the gather kernels)
+  cpu_baseline  the UNMODIFIED reference (baseline/_ref; the oracle port if it is absent) on a bounded,
+                frame-wide sample of the same workload, all host threads
+  --impl reference  times only that CPU leg
+  pde_262144, chessboard_eval_t1.0, fan_mask_render   BASELINE.json configs[2..4] (extra keys)
+Multi-GPU: STRONG scaling — the same frame for every world size, the reference's 2 048-ray chunks dealt
+round-robin to the ranks, ONE in-place all-reduce of the gradient buffer per step; `weak` (every rank a
+whole frame) and `strong_breakdown` are extra keys.
 """
 from __future__ import annotations
 
