@@ -493,7 +493,10 @@ def run_gpu(args):
                 if bound == "tensor16":   # FP16-split path: the denominator is the measured 16-bit dense peak
                     ach = work / sec / 1e12
                     e.update(bound="tensor", achieved=ach, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
-                             frac=ach / pk["bf16_tflops_sustained"], mma_per_gemm=3)
+                             frac=ach / pk["bf16_tflops_sustained"], mma_per_gemm=3,
+                             # FLOPs the tensor cores actually execute (3 MMAs per algorithmic GEMM) against the
+                             # same peak: how busy the MMA pipe is kept, as opposed to how much useful work it does
+                             mma_executed_tflops=3 * ach, mma_executed_frac=3 * ach / pk["bf16_tflops_sustained"])
                 elif bound == "tensor":
                     ach = work / sec / 1e12
                     e.update(bound="tensor", achieved=ach, peak=tf32_peak, unit="TFLOP/s", frac=ach / tf32_peak)
