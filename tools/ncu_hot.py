@@ -17,6 +17,11 @@ out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--kernel-
 lines = out.split("\n")
 start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
 rows = list(csv.DictReader(io.StringIO("\n".join(lines[start:]))))
+# a regex that matches several launches repeats the header: keep the first launch only
+for i, r in enumerate(rows):
+    if r.get("Address") == "Address":
+        rows = rows[:i]
+        break
 stall_cols = [c for c in rows[0].keys() if c.startswith("stall_") and "Not Issued" not in c]
 tot = sum(int(r["# Samples"] or 0) for r in rows)
 print(f"# {kern}: {len(rows)} instructions, {tot} stall samples")
