@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NVFI_ABI_VERSION 11
+#define NVFI_ABI_VERSION 12
 
 /* error codes */
 #define NVFI_OK 0
@@ -177,6 +177,16 @@ typedef struct NvfiRenderBuffers {
                             sample, saved by a training forward so that the backward pass need not re-evaluate
                             the first velocity evaluation to find it (used when the call has ONE step); NULL =
                             recompute */
+  /* Optional pair (both or neither), n_rays entries each: EARLY RAY TERMINATION.  With them, an advecting
+   * render in NVFI_MLP_F16X3 mode marches in depth waves; a ray whose FP32 transmittance has underflowed to
+   * exactly 0 at the end of a wave is not evaluated further — its remaining samples cannot change any output
+   * or gradient (weights = T * alpha = 0), the reference merely computes them anyway
+   * (models/tensorf_keyframe.py:641-755 has no termination).  ray_T: transmittance carried between waves;
+   * ray_term[ray]: number of leading samples that were evaluated (S if the ray never terminated).  Samples
+   * >= ray_term keep their `valid` flag (it is geometric) and get weights = sigma = 0; x_adv / x_mid are not
+   * written there. */
+  float* ray_T;
+  int32_t* ray_term;
 } NvfiRenderBuffers;
 
 /* Upstream gradients and gradient accumulators for the backward pass.  Plane

@@ -12,7 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnvfi_b200.so")
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 VEL_LAYERS = 6
 MAX_MASK_LAYERS = 8
 
@@ -69,7 +69,7 @@ class NvfiRenderBuffers(C.Structure):
         ("weights", C.c_void_p), ("mask_map", C.c_void_p), ("x_adv", C.c_void_p),
         ("valid", C.c_void_p), ("rgb", C.c_void_p), ("sigma", C.c_void_p),
         ("chunk_inside", C.c_void_p), ("counters", C.c_void_p), ("stats", C.c_void_p),
-        ("x_mid", C.c_void_p),
+        ("x_mid", C.c_void_p), ("ray_T", C.c_void_p), ("ray_term", C.c_void_p),
     ]
 
 

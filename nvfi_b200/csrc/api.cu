@@ -11,6 +11,11 @@ extern "C" int nvfi_launch_sample_advect(const NvfiField*, const NvfiRenderArgs*
                                          const NvfiRenderBuffers*, cudaStream_t);
 extern "C" int nvfi_launch_march(const NvfiField*, const NvfiRenderArgs*, const NvfiRenderBuffers*,
                                  cudaStream_t);
+extern "C" int nvfi_launch_chunk_inside(const NvfiField*, const NvfiRenderArgs*, const NvfiRenderBuffers*, cudaStream_t);
+extern "C" int nvfi_launch_sample_advect_wave(const NvfiField*, const NvfiRenderArgs*, const NvfiRenderBuffers*, int,
+                                              int, cudaStream_t);
+extern "C" int nvfi_launch_march_wave(const NvfiField*, const NvfiRenderArgs*, const NvfiRenderBuffers*, int, int,
+                                      cudaStream_t);
 extern "C" int nvfi_launch_appearance(const NvfiField*, const NvfiRenderArgs*,
                                       const NvfiRenderBuffers*, cudaStream_t);
 extern "C" int nvfi_launch_composite(const NvfiField*, const NvfiRenderArgs*,
@@ -388,10 +393,29 @@ extern "C" int nvfi_render_forward(const NvfiField* F, const NvfiRenderArgs* A,
   cudaStream_t st = (cudaStream_t)stream;
   NVFI_CUDA_OK(cudaMemsetAsync(B->counters, 0, 16 * sizeof(int32_t), st));
   if (B->stats) NVFI_CUDA_OK(cudaMemsetAsync(B->stats, 0, 4 * sizeof(int64_t), st));
-  rc = nvfi_launch_sample_advect(F, A, B, st);
-  if (rc != NVFI_OK) return rc;
-  rc = nvfi_launch_march(F, A, B, st);
-  if (rc != NVFI_OK) return rc;
+  if ((B->ray_T == nullptr) != (B->ray_term == nullptr)) return NVFI_EINVAL;
+  const int S = F->n_samples;
+  // Early ray termination (include/nvfi_b200.h, NvfiRenderBuffers.ray_T): depth waves of 32 samples (64 for
+  // long rays); each wave advects the samples of the rays that are still alive and continues their march.
+  const int wave = (S <= 256) ? 32 : 64;
+  if (B->ray_T && A->advect && mlp_mode_of(F) == NVFI_MLP_F16X3 && S > wave) {
+    rc = nvfi_launch_chunk_inside(F, A, B, st);
+    if (rc != NVFI_OK) return rc;
+    for (int s0 = 0; s0 < S; s0 += wave) {
+      const int sw = (S - s0 < wave) ? S - s0 : wave;
+      rc = nvfi_launch_sample_advect_wave(F, A, B, s0, sw, st);
+      if (rc != NVFI_OK) return rc;
+      rc = nvfi_launch_march_wave(F, A, B, s0, sw, st);
+      if (rc != NVFI_OK) return rc;
+    }
+  } else {
+    rc = nvfi_launch_sample_advect(F, A, B, st);
+    if (rc != NVFI_OK) return rc;
+    rc = nvfi_launch_march(F, A, B, st);
+    if (rc != NVFI_OK) return rc;
+    if (B->ray_term)   // not a wave render: every sample was evaluated
+      NVFI_CUDA_OK(cudaMemsetAsync(B->ray_term, 0x7f, (size_t)A->n_rays * sizeof(int32_t), st));
+  }
   rc = nvfi_launch_appearance(F, A, B, st);
   if (rc != NVFI_OK) return rc;
   return nvfi_launch_composite(F, A, B, st);

@@ -126,7 +126,9 @@ __global__ void __launch_bounds__(256)
     tail += __shfl_sync(0xffffffffu, q, 0);
     if (s < S) {
       float gs = 0.f;
-      if (B.valid[row + s]) {
+      // samples behind the point where the forward pass stopped evaluating the ray (early termination: the
+      // transmittance is exactly 0 there) have no gradient
+      if (B.valid[row + s] && (B.ray_term == nullptr || s < B.ray_term[ray])) {
         const double one_m = om[s];
         const double galpha = GT[s] - R / (one_m + 1e-10);
         float dist = 0.f;

@@ -20,9 +20,13 @@ namespace nvfi {
 
 #define MARCH_WARPS 8
 
+// Depth wave [s0, s0 + sw) of every ray (s0 a multiple of 32; the whole ray when s0 == 0 and sw >= S).  With
+// early ray termination (B.ray_T / B.ray_term, include/nvfi_b200.h) the transmittance and the partial sums
+// are carried from wave to wave; a ray whose carried transmittance is exactly 0 is finished: its later waves
+// only write zeros.
 __global__ void __launch_bounds__(MARCH_WARPS * 32, 4)
     k_march(const NvfiField F, const NvfiRenderArgs A, const NvfiRenderBuffers B, int S,
-            int s_pad) {
+            int s_pad, int s0, int sw) {
   extern __shared__ __align__(16) float sig_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long ray = (long long)blockIdx.x * MARCH_WARPS + warp;
@@ -30,10 +34,19 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, 4)
   float* sig = sig_all + warp * s_pad;
   const int g = lane >> 3, l8 = lane & 7;
   const long long row = ray * S;
-  const int n_it = (S + 31) / 32;
+  const int s_end = min(S, s0 + sw);
+  const int c_begin = s0 >> 5, n_it = (s_end + 31) / 32;
+  const bool waves = B.ray_T != nullptr;
+  if (waves && s0 > 0 && B.ray_term[ray] != S) {   // terminated in an earlier wave
+    for (int s = s0 + lane; s < s_end; s += 32) {
+      B.weights[row + s] = 0.f;
+      if (B.sigma) B.sigma[row + s] = 0.f;
+    }
+    return;
+  }
 
   // ---- density gather for the valid samples of this ray
-  for (int c = 0; c < n_it; ++c) {
+  for (int c = c_begin; c < n_it; ++c) {
     const int s = c * 32 + lane;
     const bool v = (s < S) && (B.valid[row + s] != 0);
     if (s < s_pad) sig[s] = 0.f;
@@ -75,9 +88,9 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, 4)
   const float u = train ? __ldg(A.jitter + ray) : 0.f;
 
   // ---- alpha, transmittance (exclusive product scan), weights, acc, depth
-  float carry = 1.f, acc = 0.f, dep = 0.f;
+  float carry = (waves && s0 > 0) ? B.ray_T[ray] : 1.f, acc = 0.f, dep = 0.f;
   unsigned n_app = 0;
-  for (int c = 0; c < n_it; ++c) {
+  for (int c = c_begin; c < n_it; ++c) {
     const int s = c * 32 + lane;
     float alpha = 0.f, z = 0.f, sg = 0.f;
     if (s < S) {
@@ -115,8 +128,21 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, 4)
   acc = warp_sum(acc);
   dep = warp_sum(dep);
   if (lane == 0) {
-    B.acc_map[ray] = acc;
-    B.depth_map[ray] = dep + (1.f - acc) * F.far;
+    if (!waves) {
+      B.acc_map[ray] = acc;
+      B.depth_map[ray] = dep + (1.f - acc) * F.far;
+    } else {
+      // running sums in acc_map / depth_map (the depth without its background term until the ray is finished)
+      if (s0 > 0) {
+        acc += B.acc_map[ray];
+        dep += B.depth_map[ray];
+      }
+      const bool last = s_end >= S, dead = carry == 0.f;
+      B.acc_map[ray] = acc;
+      B.depth_map[ray] = (last || dead) ? dep + (1.f - acc) * F.far : dep;
+      B.ray_T[ray] = carry;
+      B.ray_term[ray] = (dead && !last) ? s_end : S;
+    }
   }
   if (B.stats) {
     const float c = warp_sum((float)n_app);
@@ -188,8 +214,18 @@ __global__ void k_feature2density(const NvfiField F, const float* __restrict__ f
 
 using namespace nvfi;
 
+extern "C" int nvfi_launch_march_wave(const NvfiField* F, const NvfiRenderArgs* A, const NvfiRenderBuffers* B,
+                                      int s0, int sw, cudaStream_t st);
 extern "C" int nvfi_launch_march(const NvfiField* F, const NvfiRenderArgs* A,
                                  const NvfiRenderBuffers* B, cudaStream_t st) {
+  NvfiRenderBuffers b = *B;   // the whole ray in one pass: no state is carried
+  b.ray_T = nullptr;
+  b.ray_term = nullptr;
+  return nvfi_launch_march_wave(F, A, &b, 0, F->n_samples, st);
+}
+
+extern "C" int nvfi_launch_march_wave(const NvfiField* F, const NvfiRenderArgs* A, const NvfiRenderBuffers* B,
+                                      int s0, int sw, cudaStream_t st) {
   const int S = F->n_samples;
   if (A->n_rays <= 0) return NVFI_OK;
   const int s_pad = ((S + 31) / 32) * 32;
@@ -200,7 +236,7 @@ extern "C" int nvfi_launch_march(const NvfiField* F, const NvfiRenderArgs* A,
     if (rc != NVFI_OK) return rc;
   }
   const long long grid = (A->n_rays + MARCH_WARPS - 1) / MARCH_WARPS;
-  NVFI_LAUNCH(k_march, (unsigned)grid, MARCH_WARPS * 32, smem, st, *F, *A, *B, S, s_pad);
+  NVFI_LAUNCH(k_march, (unsigned)grid, MARCH_WARPS * 32, smem, st, *F, *A, *B, S, s_pad, s0, sw);
   return (int)cudaGetLastError();
 }
 

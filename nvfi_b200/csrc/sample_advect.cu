@@ -349,7 +349,11 @@ __device__ inline void advect_tile2_with(const NvfiField& F, AdvectTile (&T)[2],
 
 __global__ void __launch_bounds__(th::kLaunchThreads, 1)
     k_sample_advect_h(const __grid_constant__ NvfiField F, const NvfiRenderArgs A,
-                      const NvfiRenderBuffers B, int S, long long total, int n_batches, int mode, int subs) {
+                      const NvfiRenderBuffers B, int S, long long total, int n_batches, int mode, int subs,
+                      int s0, int sw) {
+  // Depth wave [s0, s0 + sw) of every ray (the whole ray when sw == S): raw index w -> ray w / sw, sample
+  // s0 + w % sw.  From the second wave on a ray that has terminated (ray_term != S) is not advected; its
+  // `valid` flags are still written (they are geometric).
   extern __shared__ __align__(16) unsigned char smem_raw[];
   HMlp mlp;
   mlp.init(smem_raw, F.vel_net, nullptr, mode);
@@ -363,9 +367,10 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
   int sub = subs;
   long long batch_base = 0;
   bool exhausted = false;
-  unsigned n_valid = 0;
+  unsigned n_valid = 0, n_geo = 0;
   int qc = 0, par = 0;
   const float off0 = __fsub_rn(A.t, A.base_time);
+  const bool check_term = (s0 > 0) && (B.ray_term != nullptr);
 
   for (;;) {
     // ---- produce: fill the queue up to two tiles
@@ -386,9 +391,14 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
       ++sub;
       bool push = false;
       float xn[3] = {0.f, 0.f, 0.f};
+      long long gi = 0;
       if (tid < NT && idx < total) {
-        push = eval_sample(F, A, B, idx, S, xn);
-        B.valid[idx] = push ? 1 : 0;
+        const long long ray = idx / sw;
+        gi = ray * S + s0 + (idx - ray * sw);
+        push = eval_sample(F, A, B, gi, S, xn);
+        B.valid[gi] = push ? 1 : 0;
+        n_geo += push ? 1u : 0u;
+        if (push && check_term && B.ray_term[ray] != S) push = false;
       }
       const unsigned bal = __ballot_sync(0xffffffffu, push);
       if (lane == 0 && warp < NT / 32) sm.warp_cnt[par][warp] = __popc(bal);
@@ -396,7 +406,7 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
       if (push) {
         int pos = qc + __popc(bal & ((1u << lane) - 1u));
         for (int w = 0; w < warp; ++w) pos += sm.warp_cnt[par][w];
-        sm.q_idx[pos] = (int)idx;
+        sm.q_idx[pos] = (int)gi;
         sm.q_x[0][pos] = xn[0];
         sm.q_x[1][pos] = xn[1];
         sm.q_x[2][pos] = xn[2];
@@ -446,12 +456,10 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
     __syncthreads();
   }
   mlp.finish();
-  if (B.stats) {
-    float c = warp_sum((float)n_valid);
-    if (lane == 0 && c > 0.f) {
-      atomicAdd(reinterpret_cast<unsigned long long*>(B.stats), (unsigned long long)c);
-      atomicAdd(reinterpret_cast<unsigned long long*>(B.stats) + 1, (unsigned long long)c);
-    }
+  if (B.stats) {   // [0] in-box samples, [1] samples advected (fewer with early ray termination)
+    const float c = warp_sum((float)n_valid), cg = warp_sum((float)n_geo);
+    if (lane == 0 && cg > 0.f) atomicAdd(reinterpret_cast<unsigned long long*>(B.stats), (unsigned long long)cg);
+    if (lane == 0 && c > 0.f) atomicAdd(reinterpret_cast<unsigned long long*>(B.stats) + 1, (unsigned long long)c);
   }
 }
 
@@ -641,15 +649,41 @@ static bool has_himg(const NvfiLinear* net) {
   return true;
 }
 
+// One depth wave [s0, s0 + sw) of the product path (nvfi_render_forward's early-termination loop).
+extern "C" int nvfi_launch_sample_advect_wave(const NvfiField* F, const NvfiRenderArgs* A,
+                                              const NvfiRenderBuffers* B, int s0, int sw, cudaStream_t st) {
+  const int S = F->n_samples;
+  const long long total = (long long)A->n_rays * sw;
+  if (total <= 0) return NVFI_OK;
+  if ((long long)A->n_rays * S >= (1ll << 31)) return NVFI_EUNSUPPORTED;
+  if (!has_himg(F->vel_net)) return NVFI_EINVAL;
+  NVFI_CUDA_OK(cudaMemsetAsync(B->counters, 0, sizeof(int32_t), st));   // the batch counter of this wave
+  const int subs = grab_subs(total, HMlp::kThreads, num_sms());
+  const int per_batch = subs * HMlp::kThreads;
+  const int n_batches = (int)((total + per_batch - 1) / per_batch);
+  const size_t smem = HMlp::kBytes + sizeof(SampleAdvect2Tail);
+  int rc = ensure_smem<k_sample_advect_h>(smem);
+  if (rc != NVFI_OK) return rc;
+  const int grid = min(n_batches, num_sms());
+  NVFI_LAUNCH(k_sample_advect_h, grid, HMlp::kLaunchThreads, smem, st, *F, *A, *B, S, total, n_batches,
+              NVFI_MLP_F16X3, subs, s0, sw);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int nvfi_launch_chunk_inside(const NvfiField* F, const NvfiRenderArgs* A, const NvfiRenderBuffers* B,
+                                        cudaStream_t st) {
+  const int n_chunks = (int)((A->n_rays + A->ray_chunk - 1) / A->ray_chunk);
+  NVFI_LAUNCH(k_chunk_inside, n_chunks, 256, 0, st, *F, A->rays_o, A->n_rays, A->ray_chunk, B->chunk_inside);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int nvfi_launch_sample_advect(const NvfiField* F, const NvfiRenderArgs* A,
                                          const NvfiRenderBuffers* B, cudaStream_t st) {
   const int S = F->n_samples;
   const long long total = (long long)A->n_rays * S;
   if (total <= 0) return NVFI_OK;
   if (total >= (1ll << 31)) return NVFI_EUNSUPPORTED;  // queue indices are int32
-  const int n_chunks = (int)((A->n_rays + A->ray_chunk - 1) / A->ray_chunk);
-  NVFI_LAUNCH(k_chunk_inside, n_chunks, 256, 0, st, *F, A->rays_o, A->n_rays, A->ray_chunk, B->chunk_inside);
-  NVFI_CUDA_OK(cudaGetLastError());
+  NVFI_CUDA_OK((cudaError_t)nvfi_launch_chunk_inside(F, A, B, st));
   if (!A->advect) {
     const long long blocks = (total + 255) / 256;
     const int grid = (int)(blocks < (long long)num_sms() * 16 ? blocks : (long long)num_sms() * 16);
@@ -666,7 +700,8 @@ extern "C" int nvfi_launch_sample_advect(const NvfiField* F, const NvfiRenderArg
     int rc = ensure_smem<k_sample_advect_h>(smem);
     if (rc != NVFI_OK) return rc;
     const int grid = min(n_batches, num_sms());
-    NVFI_LAUNCH(k_sample_advect_h, grid, HMlp::kLaunchThreads, smem, st, *F, *A, *B, S, total, n_batches, mode, subs);
+    NVFI_LAUNCH(k_sample_advect_h, grid, HMlp::kLaunchThreads, smem, st, *F, *A, *B, S, total, n_batches, mode, subs,
+                0, S);
     return (int)cudaGetLastError();
   }
   if (mode != NVFI_MLP_FP32_SIMT) {

@@ -400,9 +400,22 @@ def time_plan(field, t, transfer_vel: bool) -> Tuple[float, float, float, bool]:
     return float(tt), float(base), float(norm_t(tt)), False
 
 
+EARLY_TERMINATION = os.environ.get("NVFI_EARLY_TERMINATION", "1") not in ("", "0")
+
+
+def set_early_termination(on: bool) -> bool:
+    """Early ray termination of advecting renders (include/nvfi_b200.h, NvfiRenderBuffers.ray_T): samples
+    behind the point where a ray's FP32 transmittance has underflowed to exactly 0 are not advected or
+    gathered — they cannot change any output or gradient.  Off = every in-box sample is evaluated, as the
+    reference does.  Returns the previous setting."""
+    global EARLY_TERMINATION
+    prev, EARLY_TERMINATION = EARLY_TERMINATION, bool(on)
+    return prev
+
+
 class RenderOutputs:
     __slots__ = ("rgb_map", "depth_map", "acc_map", "weights", "mask_map", "x_adv", "valid", "rgb",
-                 "sigma", "chunk_inside", "counters", "stats", "args", "keep", "x_mid")
+                 "sigma", "chunk_inside", "counters", "stats", "args", "keep", "x_mid", "ray_T", "ray_term")
 
 
 def render_forward(binding: FieldBinding, rays_o: torch.Tensor, rays_d: torch.Tensor, t, *,
@@ -439,6 +452,9 @@ def render_forward(binding: FieldBinding, rays_o: torch.Tensor, rays_d: torch.Te
     o.chunk_inside = torch.empty(n_chunks, device=dev, dtype=torch.uint8)
     o.counters = torch.empty(16, device=dev, dtype=torch.int32)
     o.stats = torch.empty(4, device=dev, dtype=torch.int64) if want_stats else None
+    et = EARLY_TERMINATION and advect
+    o.ray_T = torch.empty(n, **f32) if et else None
+    o.ray_term = torch.empty(n, device=dev, dtype=torch.int32) if et else None
 
     a = L.NvfiRenderArgs()
     a.n_rays = n
@@ -473,6 +489,7 @@ def render_forward(binding: FieldBinding, rays_o: torch.Tensor, rays_d: torch.Te
     b.sigma = _ptr(o.sigma)
     b.chunk_inside, b.counters, b.stats = o.chunk_inside.data_ptr(), o.counters.data_ptr(), _ptr(o.stats)
     b.x_mid = _ptr(o.x_mid)
+    b.ray_T, b.ray_term = _ptr(o.ray_T), _ptr(o.ray_term)
     L.check(lib.nvfi_render_forward(C.byref(s), C.byref(a), C.byref(b), _stream()), "render_forward")
     o.args = (a, b)
     o.keep = (rays_o, rays_d, jitter, chunk_bg)

@@ -104,9 +104,17 @@ def test_keyframe_time_needs_no_advection(scene):
                                 ray_chunk=CHUNK, want_stats=True)
     n_valid, n_adv = int(out.stats[0]), int(out.stats[1])
     assert n_valid > 0 and n_adv == 0
-    out2 = engine.render_forward(f.binding, oo, dd, T_RENDER, white_bg=True, training=False, jitter=None,
-                                 ray_chunk=CHUNK, want_stats=True)
+    prev = engine.set_early_termination(False)      # every in-box sample is advected, as in the reference
+    try:
+        out2 = engine.render_forward(f.binding, oo, dd, T_RENDER, white_bg=True, training=False, jitter=None,
+                                     ray_chunk=CHUNK, want_stats=True)
+    finally:
+        engine.set_early_termination(prev)
     assert int(out2.stats[0]) == n_valid and int(out2.stats[1]) == n_valid
+    out3 = engine.render_forward(f.binding, oo, dd, T_RENDER, white_bg=True, training=False, jitter=None,
+                                 ray_chunk=CHUNK, want_stats=True)     # with early ray termination: fewer, same mask
+    assert int(out3.stats[0]) == n_valid and 0 < int(out3.stats[1]) < n_valid
+    assert torch.equal(out3.valid, out2.valid) and torch.equal(out3.weights, out2.weights)
 
 
 def _grads(nv, loss_fn, oo, dd, jit):
@@ -266,3 +274,46 @@ def test_extrapolated_time_gradients_vs_fp64_oracle():
     assert float((rgb.detach().double().cpu() - ref[0].detach()).abs().max()) < 1e-4
     bad = {k: v for k, v in errs.items() if not v < 1e-4}
     assert not bad, bad
+
+
+def test_early_termination_changes_nothing():
+    """Early ray termination (NvfiRenderBuffers.ray_T, engine.set_early_termination): at the headline size the
+    outputs of a train step and every gradient are the same with the samples behind a saturated surface
+    evaluated (the reference's behaviour) or skipped; only the amount of work differs."""
+    from nvfi_b200 import engine
+    from nvfi_b200.scenes import build_scene, frame_rays
+    cfg, nv, _ = build_scene("bat", grid=(199, 199, 199), step_ratio=1.79)
+    f = nv.nvfi
+    o, d = frame_rays(800, 800, theta=30.0)
+    sel = slice(300 * 800, 300 * 800 + 16384)
+    oo, dd = o[sel].cuda(), d[sel].cuda()
+    gen = torch.Generator().manual_seed(4)
+    jit = torch.rand(oo.shape[0], 1, generator=gen)
+    tgt = torch.rand(oo.shape[0], 3, generator=gen).cuda()
+    nv.requires_grad_(True)
+    f.train()
+    res = {}
+    for on in (False, True):
+        prev = engine.set_early_termination(on)
+        try:
+            nv.zero_grad(set_to_none=True)
+            out = engine.render_forward(f.binding, oo, dd, 0.33, white_bg=True, training=True, jitter=jit,
+                                        ray_chunk=2048, want_stats=True)
+            stats = out.stats.tolist()
+            rgb, depth, acc, w, _ = f.render_rays(0.33, oo, dd, white_bg=True, ray_chunk=2048, jitter=jit)
+            torch.nn.functional.mse_loss(rgb, tgt).backward()
+            res[on] = (stats, rgb.detach(), depth.detach(), acc.detach(), w.detach(),
+                       {k: p.grad.clone() for k, p in nv.named_parameters() if p.grad is not None})
+        finally:
+            engine.set_early_termination(prev)
+    s_off, s_on = res[False][0], res[True][0]
+    assert s_off[0] == s_on[0] and s_off[1] == s_off[0]        # same in-box samples; all advected without termination
+    assert s_on[1] < 0.9 * s_off[1]                             # the cube saturates: a good part of the work is skipped
+    print(f"[early termination] advected samples {s_on[1]} of {s_off[1]} ({s_on[1] / s_off[1]:.2f})")
+    assert torch.equal(res[False][4], res[True][4])             # weights: bit-identical (same scan, carried exactly)
+    for k in (1, 2, 3):     # rgb (through the background term 1 - acc) / depth / acc: the sums are formed wave by wave
+        assert float((res[False][k] - res[True][k]).abs().max()) < 2e-6 * max(1.0, float(res[False][k].abs().max()))
+    assert res[False][5].keys() == res[True][5].keys()
+    for k, g0 in res[False][5].items():
+        g1 = res[True][5][k]
+        assert float((g0 - g1).norm()) <= 2e-6 * float(g0.norm()) + 1e-30, k

@@ -114,7 +114,13 @@ def test_eval_masks_exact_vs_oracle(g, model):
     stats = out.stats.cpu()
     assert int(stats[0]) == int(aux["valid"].sum())
     assert int(stats[2]) == int(app.sum())
-    v = aux["valid"]
+    v = aux["valid"].clone()
+    if out.ray_term is not None:     # early ray termination: samples behind the end of a ray are not advected
+        S = v.shape[1]
+        v &= torch.arange(S)[None, :] < out.ray_term.cpu()[:, None]
+        assert int(stats[1]) == int(v.sum())                 # advected = in-box samples in front of the termination
+        # ... and everything that was skipped has zero weight in the reference as well
+        assert float(ref[3][aux["valid"] & ~v].abs().max() if bool((aux["valid"] & ~v).any()) else 0.0) == 0.0
     assert rel_err(out.x_adv.cpu()[v], aux["xyz_adv"][v]) < TOL
 
 
