@@ -57,9 +57,9 @@ def env_world():
 
 
 def workload_config(world):
-    return {"workload": "bat.yaml 800x800 frame per GPU, 192 samples/ray (step_ratio 1.79 @199^3), "
-                        "K=16, t=0.33 (1 RK2 step), train step = render fwd + MSE + bwd",
-            "rays_per_step_per_gpu": H * W, "samples_per_ray": 192, "grid": list(GRID),
+    return {"workload": "bat.yaml, ONE 800x800 frame per step (sharded over the GPUs), 192 samples/ray "
+                        "(step_ratio 1.79 @199^3), K=16, t=0.33 (1 RK2 step), train step = render fwd + MSE + bwd",
+            "rays_per_step": H * W, "samples_per_ray": 192, "grid": list(GRID),
             "ray_chunk": RAY_CHUNK, "parallelism": f"ray-sharded dp{world}",
             "l2": "per-sample buffers (6 GB/step) exceed L2; the 37 MB factor planes are L2-resident by design"}
 
@@ -432,6 +432,20 @@ def run_gpu(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(world), "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clk}
 
+    # ---- the same step with every in-box sample evaluated, as the reference does (early ray termination off)
+    prev_et = engine.set_early_termination(False)
+    try:
+        job.resident()
+        kk = max(1, K // 2)
+        ms_noet = timed(job.resident, kk) / kk
+    finally:
+        engine.set_early_termination(prev_et)
+    line["no_early_termination"] = {
+        "value": n_frame / (ms_noet * 1e-3), "unit": UNIT, "ms_per_step": ms_noet,
+        "note": "engine.set_early_termination(False): samples behind the point where a ray's FP32 transmittance is "
+                "exactly 0 are advected and gathered too (they cannot change any output or gradient; "
+                "tests/test_gpu_fullsize.py::test_early_termination_changes_nothing)"}
+
     # ---- the step's fixed costs beside the kernels (strong scaling exposes them): the gradient all-reduce
     if world > 1:
         ms_ar = timed(lambda: sharding.allreduce_grads(params, extras=torch.zeros(1, device=dev),
@@ -476,7 +490,7 @@ def run_gpu(args):
             "k_advect_bwd_tc": ("tensor", n_adv_bwd * 6 * VEL_EVAL_FLOP),
             "k_sample_advect_h": ("tensor16", n_adv * 2 * VEL_EVAL_FLOP),
             "k_advect_bwd_h": ("tensor16", n_adv_bwd * 6 * VEL_EVAL_FLOP),
-            "k_march": ("hbm", n_valid * DENSITY_BYTES + n * (44 + 4 * S)),
+            "k_march": ("hbm", n_adv * DENSITY_BYTES + n * (44 + 4 * S)),   # gathers only the evaluated samples
             "k_density_bwd": ("hbm", n_valid * 2 * DENSITY_BYTES),
             "k_appearance": ("hbm", n_app * APP_BYTES),
             "k_app_bwd": ("hbm", n_app_bwd * 3 * APP_BYTES),
@@ -489,6 +503,7 @@ def run_gpu(args):
             e = {"ms_per_launch": ms / cnt_l, "launches_per_step": cnt_l / P, "share": ms / total_ms}
             if name in alg:
                 bound, work = alg[name]
+                work = work / (cnt_l / P)      # per launch (the forward kernels run once per depth wave)
                 sec = (ms / cnt_l) * 1e-3
                 if bound == "tensor16":   # FP16-split path: the denominator is the measured 16-bit dense peak
                     ach = work / sec / 1e12
@@ -544,6 +559,7 @@ def run_gpu(args):
                                             "so algorithmic GB/s may exceed the HBM copy peak: see the 'l2' entry")
         line["kernels"] = kern
         line["counts"] = {"valid_samples": n_valid, "advected_samples": n_adv, "app_samples": n_app,
+                          "note": "valid = in-box samples; advected = those in front of each ray's termination",
                           "app_samples_bwd": n_app_bwd, "advected_samples_bwd": n_adv_bwd}
     for p in params:
         p.grad = None
