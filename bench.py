@@ -93,7 +93,9 @@ class CpuLeg:
         ref_path = reference_loader.find_reference(allow_checkout=False)
         if ref_path is not None:
             self.kind = "reference"
-            self.ref_models, _, self.nv = reference_loader.build_reference(ref_path, cfg, GRID, K, sd)
+            import contextlib
+            with contextlib.redirect_stdout(sys.stderr):     # the reference prints its modules while it builds them
+                self.ref_models, _, self.nv = reference_loader.build_reference(ref_path, cfg, GRID, K, sd)
             self.nv.requires_grad_(True)
             self.renderer = self.ref_models.Renderer(self.nv, 0, 0, RAY_CHUNK)
             self.field = self.nv.nvfi
@@ -187,7 +189,7 @@ def run_reference(args):
     value = r_sum / t_sum
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": 1e3 * t_sum / steps,
-            "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": leg.cores, "kind": leg.kind,
                              "sample": leg.describe(k_sum)},
