@@ -51,6 +51,25 @@ DENSITY_BYTES = 6 * 4 * 24 * 4    # 2 304 B per valid sample
 APP_BYTES = 6 * 4 * 48 * 4        # 4 608 B per appearance sample
 
 
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """Everything that libraries print to stdout while the bench runs (the reference's module dumps, NCCL's
+    version banner) goes to stderr; stdout carries exactly ONE line, written by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def env_world():
     return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
             int(os.environ.get("WORLD_SIZE", 1)))
@@ -195,7 +214,7 @@ def run_reference(args):
                              "sample": leg.describe(k_sum)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -613,7 +632,7 @@ def run_gpu(args):
                                     "sample": leg.describe(k, n_valid / float(n_frame * 192))}
         if args.rows != H:
             line["invalid_for_bench"] = f"profiling run on {args.rows} of {H} rows"
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()
@@ -722,6 +741,7 @@ def main():
                          "slow on the 6 GB full-frame working set); the line is marked invalid_for_bench")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()
+    capture_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
