@@ -653,6 +653,12 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
       if (tid < NT && idx < total && B.valid[idx]) {
         const float g0 = D.g_x_adv[idx * 3], g1 = D.g_x_adv[idx * 3 + 1], g2 = D.g_x_adv[idx * 3 + 2];
         push = (g0 != 0.f) | (g1 != 0.f) | (g2 != 0.f);
+        // A sample whose RK2 midpoint lies outside the velocity gate moved with v1 = 0: x1 = x0 whatever the
+        // network said at x0 or at the midpoint, so no gradient reaches the network through it (the adjoint
+        // seeds of both evaluations are exactly zero).  With the saved midpoints that is known here.
+        if (push && use_mid &&
+            gate_outside(F, B.x_mid[idx * 3], B.x_mid[idx * 3 + 1], B.x_mid[idx * 3 + 2]))
+          push = false;
       }
       const unsigned bal = __ballot_sync(0xffffffffu, push);
       if (lane == 0 && warp < NT / 32) T.warp_cnt[par][warp] = __popc(bal);

@@ -399,6 +399,21 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
         B.valid[gi] = push ? 1 : 0;
         n_geo += push ? 1u : 0u;
         if (push && check_term && B.ray_term[ray] != S) push = false;
+        // Outside the velocity gate the field is zero: v0 = 0 puts the midpoint on x0, which is outside the gate
+        // again, so v1 = 0 and the sample does not move — in every RK2 step, exactly (x - dt * 0 = x).  No
+        // network evaluation is needed to know that.
+        if (push && gate_outside(F, xn[0], xn[1], xn[2])) {
+          B.x_adv[gi * 3 + 0] = xn[0];
+          B.x_adv[gi * 3 + 1] = xn[1];
+          B.x_adv[gi * 3 + 2] = xn[2];
+          if (B.x_mid != nullptr) {
+            B.x_mid[gi * 3 + 0] = xn[0];
+            B.x_mid[gi * 3 + 1] = xn[1];
+            B.x_mid[gi * 3 + 2] = xn[2];
+          }
+          ++n_valid;   // counted with the advected samples (advected by a zero velocity)
+          push = false;
+        }
       }
       const unsigned bal = __ballot_sync(0xffffffffu, push);
       if (lane == 0 && warp < NT / 32) sm.warp_cnt[par][warp] = __popc(bal);
