@@ -488,7 +488,8 @@ def run_gpu(args):
         out = engine.render_forward(field.binding, job.o_d, job.d_d, T_RENDER, white_bg=True, training=True,
                                     jitter=job.jitter_d, ray_chunk=RAY_CHUNK, want_stats=True)
         torch.cuda.synchronize()
-        n_valid, n_adv, n_app, _ = (int(x) for x in out.stats.tolist())
+        n_valid, n_adv, n_app, n_mlp = (int(x) for x in out.stats.tolist())
+        n_mlp = n_mlp or n_adv
         del out
         _lib.profile_read(reset=True)
         _lib.profile_enable(True)
@@ -509,7 +510,7 @@ def run_gpu(args):
             "k_sample_advect_tc": ("tensor", n_adv * 2 * VEL_EVAL_FLOP),
             "k_advect_bwd": ("tensor", n_adv_bwd * 6 * VEL_EVAL_FLOP),   # 2 evals: fwd recompute + dX + dW GEMMs
             "k_advect_bwd_tc": ("tensor", n_adv_bwd * 6 * VEL_EVAL_FLOP),
-            "k_sample_advect_h": ("tensor16", n_adv * 2 * VEL_EVAL_FLOP),
+            "k_sample_advect_h": ("tensor16", n_mlp * 2 * VEL_EVAL_FLOP),
             "k_advect_bwd_h": ("tensor16", n_adv_bwd * 6 * VEL_EVAL_FLOP),
             "k_march": ("hbm", n_adv * DENSITY_BYTES + n * (44 + 4 * S)),   # gathers only the evaluated samples
             "k_density_bwd": ("hbm", n_valid * 2 * DENSITY_BYTES),
@@ -579,8 +580,9 @@ def run_gpu(args):
                                        note="TensoRF density gather + alpha scan; planes are L2-resident, "
                                             "so algorithmic GB/s may exceed the HBM copy peak: see the 'l2' entry")
         line["kernels"] = kern
-        line["counts"] = {"valid_samples": n_valid, "advected_samples": n_adv, "app_samples": n_app,
-                          "note": "valid = in-box samples; advected = those in front of each ray's termination",
+        line["counts"] = {"valid_samples": n_valid, "advected_samples": n_adv, "mlp_samples": n_mlp, "app_samples": n_app,
+                          "note": "valid = in-box samples; advected = those in front of each ray's termination; mlp = advected "
+                                  "samples inside the velocity gate (the others do not move)",
                           "app_samples_bwd": n_app_bwd, "advected_samples_bwd": n_adv_bwd}
     for p in params:
         p.grad = None

@@ -172,7 +172,9 @@ typedef struct NvfiRenderBuffers {
   int32_t* counters;     /* >= 16 ints (8-byte aligned), zeroed by the callee.  After
                             nvfi_render_backward, the int64 at [8] / [10] holds the number of
                             samples back-propagated through the appearance / velocity nets */
-  int64_t* stats;        /* >= 4: [valid samples, advected samples, app samples, 0], or NULL */
+  int64_t* stats;        /* >= 4: [in-box samples, advected samples (those in front of each ray's termination),
+                            app samples, samples sent through the velocity MLP (advected minus those outside the
+                            velocity gate, which do not move); 0 for the non-product arithmetic modes], or NULL */
   float* x_mid;          /* optional (n_rays, S, 3): RK2 midpoint of the last advection step of every valid
                             sample, saved by a training forward so that the backward pass need not re-evaluate
                             the first velocity evaluation to find it (used when the call has ONE step); NULL =

@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
   int sub = subs;
   long long batch_base = 0;
   bool exhausted = false;
-  unsigned n_valid = 0, n_geo = 0;
+  unsigned n_valid = 0, n_geo = 0, n_gate = 0;
   int qc = 0, par = 0;
   const float off0 = __fsub_rn(A.t, A.base_time);
   const bool check_term = (s0 > 0) && (B.ray_term != nullptr);
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
             B.x_mid[gi * 3 + 1] = xn[1];
             B.x_mid[gi * 3 + 2] = xn[2];
           }
-          ++n_valid;   // counted with the advected samples (advected by a zero velocity)
+          ++n_gate;    // counted with the advected samples (advected by a zero velocity), not with the MLP's
           push = false;
         }
       }
@@ -471,10 +471,12 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
     __syncthreads();
   }
   mlp.finish();
-  if (B.stats) {   // [0] in-box samples, [1] samples advected (fewer with early ray termination)
-    const float c = warp_sum((float)n_valid), cg = warp_sum((float)n_geo);
+  if (B.stats) {   // [0] in-box samples, [1] samples advected (fewer with early ray termination), [3] of those: by the MLP
+    const float c = warp_sum((float)n_valid), cg = warp_sum((float)n_geo), cz = warp_sum((float)n_gate);
     if (lane == 0 && cg > 0.f) atomicAdd(reinterpret_cast<unsigned long long*>(B.stats), (unsigned long long)cg);
-    if (lane == 0 && c > 0.f) atomicAdd(reinterpret_cast<unsigned long long*>(B.stats) + 1, (unsigned long long)c);
+    if (lane == 0 && c + cz > 0.f)
+      atomicAdd(reinterpret_cast<unsigned long long*>(B.stats) + 1, (unsigned long long)(c + cz));
+    if (lane == 0 && c > 0.f) atomicAdd(reinterpret_cast<unsigned long long*>(B.stats) + 3, (unsigned long long)c);
   }
 }
 
