@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnvfi_b200.so")
+# NVFI_LIB_PATH: development only (A/B timing of library variants, tools/build_variant.sh)
+LIB_PATH = os.environ.get("NVFI_LIB_PATH") or os.path.join(_HERE, "libnvfi_b200.so")
 
 ABI_VERSION = 12
 VEL_LAYERS = 6

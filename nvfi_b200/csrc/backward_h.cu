@@ -46,21 +46,37 @@
 
 #ifdef NVFI_TIMELINE
 // (tag, clock64) pairs of CTA 0: who = 0 -> worker thread 0 (first half of the buffer), who = 1 -> lane 0 of
-// the issuer warp (second half)
+// the issuer warp (second half).  Buffer pointer and counters live in shared memory, so that a mark is one
+// shared-memory round trip and one fire-and-forget 16-byte store (with everything in global memory a mark
+// cost ~400 cycles).  Recording starts with the 20th tile (warm caches, steady state).
 __device__ long long* g_tlh_buf = nullptr;
 __device__ int g_tlh_cap = 0;
 __device__ int g_tlh_n[2] = {0, 0};
-__device__ __forceinline__ void tlh_mark(int tag, int who) {
-  if (blockIdx.x == 0 && threadIdx.x == (who ? 512 : 0) && g_tlh_buf != nullptr) {
-    const int i = g_tlh_n[who], half = g_tlh_cap / 2;
-    if (i + 2 <= half) {
-      g_tlh_buf[who * half + i] = tag;
-      g_tlh_buf[who * half + i + 1] = clock64();
-      g_tlh_n[who] = i + 2;
+__shared__ long long* tl_ptr[2];
+__shared__ int tl_cnt[2], tl_max, tl_tiles;
+__device__ __forceinline__ void tlh_mark_at(int tag, int who, long long clk) {
+  if (blockIdx.x == 0 && threadIdx.x == (who ? 512 : 0)) {
+    if (tag == 0) ++tl_tiles;
+    const int i = tl_cnt[who];
+    if (i < tl_max && tl_tiles >= 20) {
+      *reinterpret_cast<longlong2*>(tl_ptr[who] + 2 * i) = make_longlong2((long long)tag, clk);
+      tl_cnt[who] = i + 1;
     }
   }
 }
-#define NVFI_TLH(tag, who) tlh_mark((tag), (who))
+#define NVFI_TLH(tag, who) tlh_mark_at((tag), (who), clock64())
+// pseudo-event with a given time stamp (e.g. the latest arrival of the 16 worker warps on a barrier)
+#define NVFI_TLH_AT(tag, who, clk) tlh_mark_at((tag), (who), (clk))
+__device__ __forceinline__ void tlh_init() {
+  if (threadIdx.x == 0) {
+    const int half = g_tlh_cap / 2;
+    tl_ptr[0] = g_tlh_buf;
+    tl_ptr[1] = g_tlh_buf + half;
+    tl_cnt[0] = tl_cnt[1] = 0;
+    tl_max = (blockIdx.x == 0 && g_tlh_buf != nullptr) ? half / 2 : 0;
+    tl_tiles = 0;
+  }
+}
 #endif
 #include "mlp_h.cuh"
 
@@ -157,6 +173,7 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
                            float (&acc_bias)[6], const float* __restrict__ stash_s2 = nullptr) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool value_row = !JVP || (lane < 30 && lane % 5 == 0);
+  NVFI_TLH(98, 0);
   const uint32_t gw_hi = tc::smem_u32(T.gw_hi), gw_lo = tc::smem_u32(T.gw_lo);
 
   // ---- scale of the tile: largest |dL/dw| -> [8, 16)
@@ -228,18 +245,27 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
       tc::mbar_expect_tx(&c.abar, th::kTileBytes);
       tc::bulk_g2s_u32(tA, stash_a + 32768 + (size_t)3 * th::kTileBytes, th::kTileBytes, &c.abar);   // A_3
     }
-    __syncwarp();
-    th::ring_top_up(c, is, false);
-    __syncthreads();   // (B) G_4 in tile tG
-    tc::tc_fence_after();
-    NVFI_TLH(1104, 1);
     // dX of layer l: D0[m][k] = sum_n G_l[m][n] W_l[n][k]
+    // Both K blocks of W_l^T are awaited BEFORE the block barrier that publishes G_l (dx_ready), so that after
+    // the barrier the MMAs are issued without a single load/store-unit instruction: the 16 worker warps start
+    // the dW flush right behind that barrier, and an mbarrier probe of this warp then queues behind their
+    // reductions (phase timeline: the issue of dX(l - 1) used to last exactly as long as the flush of layer l).
+    auto dx_ready = [&]() {
+#ifndef NVFI_BWD_NO_PREACQUIRE
+      th::ring_wait(c, is, 0);
+      th::ring_wait(c, is, 1);
+#endif
+    };
     auto issue_dx = [&](int l) {
       const uint32_t nx = (l == 0) ? 32u : 128u;
       const uint32_t idx = (l == 0) ? id32 : id128;
 #pragma unroll 1
       for (uint32_t kb = 0; kb < 2; ++kb) {
+#ifndef NVFI_BWD_NO_PREACQUIRE
+        const uint32_t st = is.ring_u32 + is.c_stage * th::kStageBytes;   // awaited by dx_ready()
+#else
         const uint32_t st = th::ring_acquire(c, is);
+#endif
         if (tc::elect_one()) {
 #pragma unroll
           for (uint32_t ks = 0; ks < 4; ++ks) {
@@ -257,6 +283,12 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
         th::ring_advance(is);
       }
     };
+    __syncwarp();
+    th::ring_top_up(c, is, false);
+    dx_ready();
+    __syncthreads();   // (B) G_4 in tile tG
+    tc::tc_fence_after();
+    NVFI_TLH(1104, 1);
     issue_dx(4);
 #pragma unroll 1
     for (int l = 4; l >= 0; --l) {
@@ -281,10 +313,18 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
       }
       __syncwarp();
       NVFI_TLH(1120 + l, 1);
-      th::ring_top_up(c, is, false);        // dX(l) is done by now: its stages take the next layer's W^T blocks
+#ifndef NVFI_BWD_NO_PREACQUIRE
+      th::ring_top_up(c, is, true);         // as soon as dX(l) has completed its stages take the next W^T blocks
+      NVFI_TLH(1160 + l, 1);
       tc::mbar_wait(&c.wbar, wphase & 1);   // dW(l) done: tile tA is free for A_{l-2}
       ++wphase;
+      NVFI_TLH(1170 + l, 1);
+#else
       th::ring_top_up(c, is, false);
+      tc::mbar_wait(&c.wbar, wphase & 1);
+      ++wphase;
+      th::ring_top_up(c, is, false);
+#endif
       if (l > 0 && tc::elect_one()) {
         if (l >= 2) {
           tc::mbar_expect_tx(&c.abar, th::kTileBytes);
@@ -296,6 +336,7 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
         }
       }
       __syncwarp();
+      if (l > 0) dx_ready();                // W_{l-1}^T has landed: nothing but MMAs behind the barrier
       NVFI_TLH(1130 + l, 1);
       __syncthreads();   // (C1) G_{l-1} in tile tG
       tc::tc_fence_after();
@@ -540,7 +581,9 @@ __device__ void bwd_eval_h(th::Ctl1& c, th::Issuer& is_shared, BwdTile& T, uint3
     tc::tc_fence_before();   // the D1 reads are ordered before the next barrier (the issuer reuses D1 two layers on)
     NVFI_TLH(160 + L, 0);
   }
+  NVFI_TLH(170, 0);
   asm volatile("fence.proxy.async.global;" ::: "memory");   // the next evaluation's bulk copies rewrite the discarded lines
+  NVFI_TLH(171, 0);
 }
 
 // v = basis(w, x): dL/dw and the explicit dL/dx from dL/dv (as in backward.cu)
@@ -595,6 +638,9 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
 
   // with the midpoints saved by the forward pass (single-step calls) the evaluation that only finds them is skipped
   const bool use_mid = (B.x_mid != nullptr) && n_steps == 1;
+#ifdef NVFI_TIMELINE
+  tlh_init();
+#endif
   th::setup(ctl, F.vel_net, nullptr, kTmemCols);
   if (tid == 0) {   // weight segments in the order one tile consumes them
     int n = 0;
@@ -650,16 +696,33 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
       const long long idx = batch_base + (long long)sub * NT + tid;
       ++sub;
       bool push = false;
-      if (tid < NT && idx < total && B.valid[idx]) {
+#ifndef NVFI_BWD_SERIAL_SCAN
+      if (tid < NT && idx < total) {
+        // all three streams are read at once (one memory latency instead of three dependent ones; the values
+        // of samples that are not valid are never used: both buffers are fully allocated)
+        const unsigned char v = B.valid[idx];
         const float g0 = D.g_x_adv[idx * 3], g1 = D.g_x_adv[idx * 3 + 1], g2 = D.g_x_adv[idx * 3 + 2];
-        push = (g0 != 0.f) | (g1 != 0.f) | (g2 != 0.f);
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+        if (use_mid) {
+          m0 = B.x_mid[idx * 3];
+          m1 = B.x_mid[idx * 3 + 1];
+          m2 = B.x_mid[idx * 3 + 2];
+        }
+        push = v && ((g0 != 0.f) | (g1 != 0.f) | (g2 != 0.f));
         // A sample whose RK2 midpoint lies outside the velocity gate moved with v1 = 0: x1 = x0 whatever the
         // network said at x0 or at the midpoint, so no gradient reaches the network through it (the adjoint
         // seeds of both evaluations are exactly zero).  With the saved midpoints that is known here.
+        if (push && use_mid && gate_outside(F, m0, m1, m2)) push = false;
+      }
+#else
+      if (tid < NT && idx < total && B.valid[idx]) {
+        const float g0 = D.g_x_adv[idx * 3], g1 = D.g_x_adv[idx * 3 + 1], g2 = D.g_x_adv[idx * 3 + 2];
+        push = (g0 != 0.f) | (g1 != 0.f) | (g2 != 0.f);
         if (push && use_mid &&
             gate_outside(F, B.x_mid[idx * 3], B.x_mid[idx * 3 + 1], B.x_mid[idx * 3 + 2]))
           push = false;
       }
+#endif
       const unsigned bal = __ballot_sync(0xffffffffu, push);
       if (lane == 0 && warp < NT / 32) T.warp_cnt[par][warp] = __popc(bal);
       const int tot = __syncthreads_count(push);
@@ -684,6 +747,14 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
       const long long gi = live ? T.q_idx[start + tid] : 0;
       T.gidx[tid] = (int)gi;
       float xn[3] = {0.f, 0.f, 0.f};
+      float gb[3] = {0.f, 0.f, 0.f}, xmv[3] = {0.f, 0.f, 0.f};   // loaded first: independent of the ray's loads
+      if (live) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          gb[a] = D.g_x_adv[gi * 3 + a];
+          if (use_mid) xmv[a] = B.x_mid[gi * 3 + a];
+        }
+      }
       if (live) {
         const long long ray = gi / S;
         const int s = (int)(gi - ray * S);
@@ -700,12 +771,13 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         T.x0[a][tid] = xn[a];
-        T.gbar[a][tid] = live ? D.g_x_adv[gi * 3 + a] : 0.f;
-        if (use_mid) T.xm[a][tid] = live ? B.x_mid[gi * 3 + a] : 0.f;
+        T.gbar[a][tid] = gb[a];
+        if (use_mid) T.xm[a][tid] = xmv[a];
       }
       T.gate0[tid] = gate_outside(F, xn[0], xn[1], xn[2]);
     }
     __syncthreads();
+    NVFI_TLH(2, 0);
 
 #pragma unroll 1
     for (int op = 0; op < n_ops; ++op) {
@@ -751,6 +823,7 @@ __global__ void __launch_bounds__(th::kLaunchThreads, 1)
                                     st ? stash_a : nullptr, st ? stash_s : nullptr);
       }
       // ---- glue after the evaluation
+      NVFI_TLH(4, 0);
       if (tid < NVFI_TM) {
         const int m = tid;
         if (kind == K_FWD_A || kind == K_REV_A0) {   // midpoint m = x0 - dt/2 v0(x0)

@@ -409,6 +409,11 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool stash = stash_a != nullptr;
   if (tile1_u32 == 0u) tile1_u32 = tile_u32;
+#ifdef NVFI_TLH_AT
+  __shared__ volatile long long tl_arr[16];
+  __shared__ volatile long long tl_iss[10];
+  __shared__ volatile long long tl_own[4];
+#endif
   // layer L reads tile (L & 1), its epilogue writes tile ((L + 1) & 1)
   if (warp == kIssuerWarp) {      // ---- issuer warp: all 32 lanes run the issue code uniformly
     Issuer is = is_ref;
@@ -432,6 +437,10 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
         ring_top_up(c, is, false);
         tc::mbar_wait(&c.kready[g], kphase & 1);
         tc::tc_fence_after();
+        NVFI_TLH(1200 + 4 * l + (int)g, 1);
+#ifdef NVFI_TLH_AT
+        tl_iss[2 + 2 * g] = clock64();   // woken on kready[g]
+#endif
         const bool st = stash && l < 4 && g == 3;
         if (st && tc::elect_one()) {   // A_l is complete: copy the tile image to the stash
           bulk_s2g(stash_a + 32768 + (size_t)l * kTileBytes, ((l + 1) & 1) ? tile1_u32 : tile_u32, kTileBytes);
@@ -443,6 +452,15 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
         issue_group<TS>(c, is, ((l + 1) & 1) ? tile1_u32 : tile_u32, l + 1, g, stage, g == 3,
                     (stash && g == 3) ? (tile1_u32 == tile_u32 ? 1 : 2) : 0);
         NVFI_TLH(1020 + 4 * l + (int)g, 1);
+#ifdef NVFI_TLH_AT
+        tl_iss[3 + 2 * g] = clock64();   // group g issued
+        if (g == 3) {   // timeline builds: when does the tensor pipe publish layer l + 1's accumulator?
+          tl_iss[0] = clock64();   // commit issued
+          tc::mbar_wait(&c.dbar, (dphase + (uint32_t)l + 1u) & 1);
+          tl_iss[1] = clock64();   // accumulator published, as seen by the issuer
+          NVFI_TLH(1500 + l, 1);
+        }
+#endif
       }
       ++kphase;
     }
@@ -507,13 +525,36 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
     tc::mbar_wait(&c.dbar, dphase & 1);
     ++dphase;
     tc::tc_fence_after();
+#ifdef NVFI_TLH_AT
+    const long long t_wake = clock64();
+    if (l > 0 && tid == 0) {   // the latest of the 16 warps' arrivals that released layer l's last MMAs
+      long long mx = 0;
+      for (int w = 0; w < 16; ++w) mx = tl_arr[w] > mx ? tl_arr[w] : mx;
+      NVFI_TLH_AT(200 + l, 0, mx);
+      if (l == 2) {   // one layer in detail: arrivals of this thread's warp, wake-ups and issues of the issuer
+        for (int g = 0; g < 4; ++g) {
+          NVFI_TLH_AT(500 + g, 0, tl_own[g]);
+          NVFI_TLH_AT(510 + g, 0, tl_iss[2 + 2 * g]);
+          NVFI_TLH_AT(520 + g, 0, tl_iss[3 + 2 * g]);
+        }
+      }
+      NVFI_TLH_AT(300 + l, 0, tl_iss[0]);
+      NVFI_TLH_AT(400 + l, 0, tl_iss[1]);
+    }
+    NVFI_TLH_AT(20 + l, 0, t_wake);
+#else
     NVFI_TLH(20 + l, 0);
+#endif
     const uint32_t dcol = tb + lane_base + kColD + 128u * (uint32_t)(l & 1) + (uint32_t)(h * 8);
     uint32_t raw[4][8];
 #pragma unroll
     for (int g = 0; g < 4; ++g) tc::tmem_ld8_nowait(dcol + 32u * g, raw[g]);
     tc::tmem_ld_wait();
-    // ---- epilogue, one 32-column group of layer l + 1's A operand at a time
+    // ---- epilogue, one 32-column group of layer l + 1's A operand at a time.  (The loop is unrolled and ptxas
+    // hoists the activations of all four groups in front of the first group's stores, so the 16 warps arrive
+    // on kready[0..3] late in the epilogue; a loop that is NOT unrolled keeps the groups staged — arrivals
+    // ~1 K cycles apart — but loses the instruction-level parallelism: measured time-neutral, as was handing
+    // the operand over in two halves instead of four groups.)
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const int col = g * 32 + h * 8;
@@ -568,6 +609,10 @@ __device__ void vel_net_tile_h(C& c, Issuer& is_ref, int which, float* outS, con
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&c.kready[g]);
+#ifdef NVFI_TLH_AT
+      if (g == 3 && lane == 0) tl_arr[warp] = clock64();
+      if (tid == 0) tl_own[g] = clock64();
+#endif
     }
     ++kphase;
     NVFI_TLH(30 + l, 0);

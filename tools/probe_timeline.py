@@ -20,7 +20,7 @@ def step():
     rgb, *_ = f.render_rays(0.33, o, d, white_bg=True, ray_chunk=2048, jitter=jit)
     torch.nn.functional.mse_loss(rgb, target).backward()
 step(); torch.cuda.synchronize()
-buf = torch.zeros(40000, dtype=torch.int64, device="cuda")
+buf = torch.zeros(80000, dtype=torch.int64, device="cuda")
 lib.nvfi_debug_timeline(buf.data_ptr(), buf.numel())
 step(); torch.cuda.synchronize()
 lib.nvfi_debug_timeline(None, 0)
@@ -40,7 +40,7 @@ for who, bb in parts:
     for (t0, c0), (t1, c1) in zip(ev, ev[1:]):
         d[(t0, t1)].append(c1 - c0)
     tot = sum(sum(v) for v in d.values())
-    for k in sorted(d, key=lambda k: -sum(d[k]))[:45]:
+    for k in sorted(d, key=lambda k: -sum(d[k]))[:int(os.environ.get('TL_TOP', '70'))]:
         v = d[k]
         print(f"{k[0]:5d}->{k[1]:5d}  n={len(v):4d} mean {sum(v)/len(v):9.0f} cyc  share {100*sum(v)/tot:5.1f}%")
     tiles = [c for t, c in ev if t == 0]
