@@ -22,6 +22,11 @@ KEYS = [
     "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg",
     "sm__inst_executed_pipe_tc.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "smsp__inst_executed_pipe_xu.sum", "smsp__inst_executed_pipe_fma.sum",
+    # the SM <-> L2 path (what the stash, the weight ring and the dW reductions of the MLP kernels load)
+    "l1tex__m_l1tex2xbar_write_bytes.sum", "l1tex__m_l1tex2xbar_write_bytes.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sectors.sum", "lts__t_sectors_srcunit_tex_op_red.sum",
+    "lts__t_sectors_srcunit_tex_op_write.sum", "lts__t_sectors_srcunit_tex_op_read.sum",
 ]
 
 
