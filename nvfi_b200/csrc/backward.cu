@@ -153,7 +153,10 @@ __device__ __forceinline__ float dsigma_dfeat(const NvfiField& F, float sigma, f
 // k_density_bwd: one warp per ray, 8-lane groups per valid sample.
 // g_x_adv[sample] = (appearance part, already written for w > thres) + density part.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 3)
+#ifndef NVFI_DBWD_BLOCKS
+#define NVFI_DBWD_BLOCKS 3   // measured against 2 and 4 resident blocks per SM
+#endif
+__global__ void __launch_bounds__(256, NVFI_DBWD_BLOCKS)
     k_density_bwd(const NvfiField F, const NvfiRenderArgs A, const NvfiRenderBuffers B,
                   const NvfiRenderGrads D, int S) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
