@@ -1,8 +1,12 @@
 """Phase timeline of CTA 0 of the tensor-core backward (clock64 deltas between marks).
 
-The marks are compiled out of the product build: rebuild the library with
-    NVFI_TIMELINE=1 python -m nvfi_b200.build --force
-before sending this probe to the GPU box (and rebuild without it afterwards)."""
+The marks are compiled out of the product build.  Build a variant with them and point the loader at it:
+    tools/build_variant.sh tl -DNVFI_TIMELINE
+    NVFI_LIB_PATH=$PWD/nvfi_b200/_variants/libtl.so python tools/probe_timeline.py      (on the GPU box)
+Marks of worker thread 0 (tags < 1000) and of the issuer warp (tags >= 1000) are taken on the same SM clock;
+tags 200+l / 300+l / 400+l are pseudo-events of a stashed forward layer: the last of the 16 kready[3]
+arrivals, the issuer's commit of the next accumulator, the moment the issuer sees it published.
+TL_TOP=n prints the n largest transitions (default 70)."""
 import sys, os, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
